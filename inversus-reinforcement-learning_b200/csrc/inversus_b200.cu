@@ -1,0 +1,578 @@
+// inversus_b200.cu -- host side of the C ABI declared in include/inversus_b200.h.
+//
+// The handle owns all device memory (packed state planes + every output buffer); callers see raw
+// device pointers through inv_get_buffer and may wrap them without copies. No torch, no
+// third-party code: CUDA runtime only. There is deliberately no CPU fallback -- every entry point
+// fails with INV_ERR_NO_DEVICE / INV_ERR_CUDA when no sm_100 device is usable.
+#include "inversus_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace inv;
+
+struct inv_sim {
+    inv_config cfg;
+    int64_t n;
+    uint4 *state;
+    void *obs1, *obs2;
+    float *extra1, *extra2, *reward;
+    uint8_t *done, *info, *dbg;
+    int32_t *ep_steps;
+    double *ep_return;
+    uint32_t *status;
+    const uint32_t *table;
+    int sm_count;
+    int64_t launches;
+    bool was_reset;
+    // staging for the *_host calls: pinned host + device copies of the action ids
+    int8_t *h_a1, *h_a2, *d_a1, *d_a2;
+    uint32_t *h_status;
+    cudaStream_t host_stream;
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, const char *a = "", const char *b = "")
+{
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess) return fail(INV_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+namespace {
+
+__global__ void init_episode_kernel(uint4 *plane2, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) plane2[i] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u); // episode = "none yet", return = 0.0
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+size_t obs_elem_bytes(int dt) { return dt == INV_OBS_F32 ? 4 : dt == INV_OBS_BF16 ? 2 : 1; }
+
+Params base_params(const inv_sim *s)
+{
+    Params p;
+    memset(&p, 0, sizeof(p));
+    p.state = s->state;
+    p.stride = s->n;
+    p.count = s->n;
+    p.table = s->table;
+    p.obs1 = s->obs1; p.obs2 = s->obs2;
+    p.extra1 = s->extra1; p.extra2 = s->extra2;
+    p.reward = s->reward; p.done = s->done; p.info = s->info; p.dbg = s->dbg;
+    p.ep_steps = s->ep_steps; p.ep_return = s->ep_return;
+    p.status = s->status;
+    p.seed_lo = (uint32_t)s->cfg.seed;
+    p.seed_hi = (uint32_t)(s->cfg.seed >> 32);
+    p.env_id_base = (uint32_t)s->cfg.env_id_base;
+    p.mode = s->cfg.mode;
+    p.difficulty = s->cfg.difficulty;
+    p.max_steps = s->cfg.max_episode_steps;
+    p.auto_reset = (s->cfg.flags & INV_FLAG_AUTO_RESET) ? 1 : 0;
+    return p;
+}
+
+// Grid: one CTA per tile up to a resident-CTA cap (a multiple of the SM count), grid-stride beyond.
+template <int OP, int DT, bool P2V, bool INDEXED, int E>
+cudaError_t launch_one(const Params &p, int sm_count, cudaStream_t st)
+{
+    auto kern = inv_kernel<OP, DT, P2V, INDEXED, E>;
+    constexpr size_t smem = smem_bytes<E, P2V, INDEXED>();
+    static int blocks_per_sm = 0; // per instantiation
+    if (blocks_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int b = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, kThreads, smem);
+        if (e != cudaSuccess) return e;
+        blocks_per_sm = b > 0 ? b : 1;
+    }
+    const int64_t ntiles = (p.count + E - 1) / E;
+    if (ntiles <= 0) return cudaSuccess;
+    const int64_t cap = (int64_t)sm_count * blocks_per_sm * 4;
+    const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+    kern<<<grid, kThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// Tile size: 128 envs per CTA for big batches; 32 (one logic warp, four store warps) when the
+// batch is too small to give every SM a 128-env tile.
+template <int OP, int DT, bool P2V, bool INDEXED>
+cudaError_t launch_e(const Params &p, int sm_count, cudaStream_t st)
+{
+    if (p.count >= (int64_t)sm_count * 128 * 2) return launch_one<OP, DT, P2V, INDEXED, 128>(p, sm_count, st);
+    return launch_one<OP, DT, P2V, INDEXED, 32>(p, sm_count, st);
+}
+
+template <int OP, bool INDEXED>
+cudaError_t launch(const Params &p, int dt, bool p2v, int sm_count, cudaStream_t st)
+{
+#define INV_CASE(DTV)                                                                   \
+    case DTV:                                                                           \
+        return p2v ? launch_e<OP, DTV, true, INDEXED>(p, sm_count, st)                  \
+                   : launch_e<OP, DTV, false, INDEXED>(p, sm_count, st);
+    switch (dt) {
+        INV_CASE(INV_OBS_F32)
+        INV_CASE(INV_OBS_BF16)
+        INV_CASE(INV_OBS_U8)
+    default:
+        return cudaErrorInvalidValue;
+    }
+#undef INV_CASE
+}
+
+// packed <-> canonical (host side; used by export/import only)
+void unpack_host(const uint32_t *pl[5], int64_t i, inv_env_state *o)
+{
+    const uint32_t *a = pl[0] + 4 * i, *b = pl[1] + 4 * i, *c = pl[2] + 4 * i, *d = pl[3] + 4 * i, *e = pl[4] + 4 * i;
+    memset(o, 0, sizeof(*o));
+    o->tiles[0] = a[0]; o->tiles[1] = a[1]; o->tiles[2] = a[2]; o->tiles[3] = a[3]; o->tiles[4] = b[0];
+    const uint32_t pw[2] = {b[1], b[2]};
+    int32_t *pp[2] = {o->p1, o->p2};
+    for (int k = 0; k < 2; ++k) {
+        pp[k][0] = pw[k] & 15; pp[k][1] = (pw[k] >> 4) & 15; pp[k][2] = (pw[k] >> 8) & 7;
+        pp[k][3] = (pw[k] >> 11) & 31; pp[k][4] = (pw[k] >> 16) & 1;
+    }
+    o->n_bullets = (b[1] >> 20) & 31;
+    o->step_count = (int32_t)b[3];
+    o->episode = c[0];
+    uint64_t bits = (uint64_t)c[1] | ((uint64_t)c[2] << 32);
+    memcpy(&o->episode_return, &bits, 8);
+    const uint32_t w[8] = {d[0], d[1], d[2], d[3], e[0], e[1], e[2], e[3]};
+    for (int s = 0; s < o->n_bullets && s < INV_MAX_BULLETS; ++s) {
+        const uint32_t bl = (w[s >> 1] >> ((s & 1) * 16)) & 0xFFFFu;
+        o->bullets[s][0] = (int8_t)(bl & 15); o->bullets[s][1] = (int8_t)((bl >> 4) & 15);
+        o->bullets[s][2] = (int8_t)((bl >> 8) & 3); o->bullets[s][3] = (int8_t)((bl >> 10) & 1);
+    }
+}
+
+bool pack_host(const inv_env_state *in, uint32_t *pl[5], int64_t i)
+{
+    uint32_t *a = pl[0] + 4 * i, *b = pl[1] + 4 * i, *c = pl[2] + 4 * i, *d = pl[3] + 4 * i, *e = pl[4] + 4 * i;
+    if (in->tiles[4] >> 22) return false;
+    if (in->n_bullets < 0 || in->n_bullets > INV_MAX_BULLETS) return false;
+    a[0] = in->tiles[0]; a[1] = in->tiles[1]; a[2] = in->tiles[2]; a[3] = in->tiles[3]; b[0] = in->tiles[4];
+    const int32_t *pp[2] = {in->p1, in->p2};
+    uint32_t pw[2];
+    for (int k = 0; k < 2; ++k) {
+        const int32_t *q = pp[k];
+        if (q[0] < 0 || q[0] >= INV_BOARD_W || q[1] < 0 || q[1] >= INV_BOARD_H || q[2] < 0 || q[2] > 7 ||
+            q[3] < 0 || q[3] > 31 || (q[4] != 0 && q[4] != 1))
+            return false;
+        pw[k] = (uint32_t)q[0] | ((uint32_t)q[1] << 4) | ((uint32_t)q[2] << 8) | ((uint32_t)q[3] << 11) | ((uint32_t)q[4] << 16);
+    }
+    b[1] = pw[0] | ((uint32_t)in->n_bullets << 20);
+    b[2] = pw[1];
+    b[3] = (uint32_t)in->step_count;
+    c[0] = in->episode;
+    uint64_t bits;
+    memcpy(&bits, &in->episode_return, 8);
+    c[1] = (uint32_t)bits; c[2] = (uint32_t)(bits >> 32); c[3] = 0;
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < in->n_bullets; ++s) {
+        const int8_t *q = in->bullets[s];
+        if (q[0] < 0 || q[0] >= INV_BOARD_W || q[1] < 0 || q[1] >= INV_BOARD_H || q[2] < 0 || q[2] > 3 || q[3] < 0 || q[3] > 1)
+            return false;
+        const uint32_t bl = (uint32_t)q[0] | ((uint32_t)q[1] << 4) | ((uint32_t)q[2] << 8) | ((uint32_t)q[3] << 10);
+        w[s >> 1] |= bl << ((s & 1) * 16);
+    }
+    d[0] = w[0]; d[1] = w[1]; d[2] = w[2]; d[3] = w[3];
+    e[0] = w[4]; e[1] = w[5]; e[2] = w[6]; e[3] = w[7];
+    return true;
+}
+
+} // namespace
+
+extern "C" {
+
+int inv_abi_version(void) { return INV_ABI_VERSION; }
+const char *inv_last_error(void) { return g_err; }
+
+int inv_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int inv_create(const inv_config *cfg, inv_sim **out)
+{
+    if (!cfg || !out) return fail(INV_ERR_INVALID_ARG, "inv_create: null argument");
+    *out = nullptr;
+    if (cfg->n_envs <= 0) return fail(INV_ERR_INVALID_ARG, "inv_create: n_envs must be positive");
+    if (cfg->mode != INV_MODE_DUMMY && cfg->mode != INV_MODE_SELFPLAY)
+        return fail(INV_ERR_INVALID_ARG, "Unknown opponent_type"); // env_wrappers.py:316
+    if (cfg->difficulty != INV_DIFFICULTY_EASY && cfg->difficulty != INV_DIFFICULTY_HARD)
+        return fail(INV_ERR_INVALID_ARG, "inv_create: difficulty must be easy(0) or hard(1)");
+    if (cfg->obs_dtype < INV_OBS_F32 || cfg->obs_dtype > INV_OBS_U8)
+        return fail(INV_ERR_INVALID_ARG, "inv_create: unknown obs_dtype");
+    if (cfg->max_episode_steps <= 0) return fail(INV_ERR_INVALID_ARG, "inv_create: max_episode_steps must be positive");
+    if (cfg->env_id_base < 0 || cfg->env_id_base + cfg->n_envs > 0xFFFFFFFFll)
+        return fail(INV_ERR_INVALID_ARG, "inv_create: global env ids must fit 32 bits");
+    int ndev = inv_device_count();
+    if (ndev <= 0) return fail(INV_ERR_NO_DEVICE, "no CUDA device: this simulator has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(INV_ERR_INVALID_ARG, "inv_create: bad device ordinal");
+    DeviceGuard g(cfg->device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(INV_ERR_NO_DEVICE, "device is not sm_100 (B200): kernels are built for sm_100a only");
+
+    inv_sim *s = new (std::nothrow) inv_sim();
+    if (!s) return fail(INV_ERR_INVALID_ARG, "out of host memory");
+    memset(s, 0, sizeof(*s));
+    s->cfg = *cfg;
+    if (cfg->mode == INV_MODE_SELFPLAY) s->cfg.flags |= INV_FLAG_P2_VIEW; // env_wrappers.py:311
+    s->n = cfg->n_envs;
+    s->sm_count = prop.multiProcessorCount;
+    const int64_t n = s->n;
+    const bool p2v = (s->cfg.flags & INV_FLAG_P2_VIEW) != 0;
+    const size_t obs_bytes = (size_t)n * INV_OBS_ELEMS * obs_elem_bytes(cfg->obs_dtype);
+#define ALLOC(ptr, bytes)                                                        \
+    do {                                                                         \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));                   \
+        if (e_ != cudaSuccess) {                                                 \
+            fail(INV_ERR_CUDA, "cudaMalloc(%s): %s", #ptr, cudaGetErrorString(e_)); \
+            inv_destroy(s);                                                      \
+            return INV_ERR_CUDA;                                                 \
+        }                                                                        \
+    } while (0)
+    ALLOC(s->state, (size_t)n * INV_PACKED_STATE_BYTES);
+    ALLOC(s->obs1, obs_bytes);
+    ALLOC(s->extra1, (size_t)n * 16);
+    if (p2v) {
+        ALLOC(s->obs2, obs_bytes);
+        ALLOC(s->extra2, (size_t)n * 16);
+    }
+    ALLOC(s->reward, (size_t)n * 4);
+    ALLOC(s->done, (size_t)n);
+    ALLOC(s->info, (size_t)n);
+    ALLOC(s->dbg, (size_t)n);
+    ALLOC(s->ep_steps, (size_t)n * 4);
+    ALLOC(s->ep_return, (size_t)n * 8);
+    ALLOC(s->status, 4);
+    ALLOC(s->d_a1, (size_t)n);
+    ALLOC(s->d_a2, (size_t)n);
+#undef ALLOC
+    // "no episode yet": zero state with episode = 0xFFFFFFFF so that the first reset starts episode 0
+    cudaMemset(s->state, 0, (size_t)n * INV_PACKED_STATE_BYTES);
+    init_episode_kernel<<<(unsigned)((n + 255) / 256), 256>>>(s->state + 2 * n, n);
+    cudaMemset(s->status, 0, 4);
+    cudaMemset(s->reward, 0, (size_t)n * 4);
+    cudaMemset(s->done, 0, (size_t)n);
+    cudaMemset(s->info, 0, (size_t)n);
+    cudaMemset(s->dbg, 0, (size_t)n);
+    cudaMemset(s->ep_steps, 0, (size_t)n * 4);
+    cudaMemset(s->ep_return, 0, (size_t)n * 8);
+    if (cudaMallocHost((void **)&s->h_a1, (size_t)n) != cudaSuccess ||
+        cudaMallocHost((void **)&s->h_a2, (size_t)n) != cudaSuccess ||
+        cudaMallocHost((void **)&s->h_status, 4) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->host_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail(INV_ERR_CUDA, "pinned staging / stream allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        inv_destroy(s);
+        return INV_ERR_CUDA;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        fail(INV_ERR_CUDA, "inv_create: %s", cudaGetErrorString(e));
+        inv_destroy(s);
+        return INV_ERR_CUDA;
+    }
+    *out = s;
+    return INV_OK;
+}
+
+int inv_destroy(inv_sim *s)
+{
+    if (!s) return INV_OK;
+    DeviceGuard g(s->cfg.device);
+    cudaDeviceSynchronize();
+    void *dev[] = {s->state, s->obs1, s->obs2, s->extra1, s->extra2, s->reward, s->done, s->info,
+                   s->dbg, s->ep_steps, s->ep_return, s->status, s->d_a1, s->d_a2};
+    for (void *p : dev)
+        if (p) cudaFree(p);
+    if (s->h_a1) cudaFreeHost(s->h_a1);
+    if (s->h_a2) cudaFreeHost(s->h_a2);
+    if (s->h_status) cudaFreeHost(s->h_status);
+    if (s->host_stream) cudaStreamDestroy(s->host_stream);
+    delete s;
+    return INV_OK;
+}
+
+int inv_get_config(const inv_sim *s, inv_config *out)
+{
+    if (!s || !out) return fail(INV_ERR_INVALID_ARG, "inv_get_config: null argument");
+    *out = s->cfg;
+    return INV_OK;
+}
+
+int inv_reset(inv_sim *s, void *stream)
+{
+    if (!s) return fail(INV_ERR_INVALID_ARG, "inv_reset: null handle");
+    DeviceGuard g(s->cfg.device);
+    Params p = base_params(s);
+    CUDA_TRY((launch<OP_RESET, false>(p, s->cfg.obs_dtype, (s->cfg.flags & INV_FLAG_P2_VIEW) != 0, s->sm_count,
+                                      (cudaStream_t)stream)));
+    s->launches += 1;
+    s->was_reset = true;
+    return INV_OK;
+}
+
+int inv_reset_envs(inv_sim *s, const int64_t *idx_dev, int64_t count, void *stream)
+{
+    if (!s || (!idx_dev && count > 0)) return fail(INV_ERR_INVALID_ARG, "inv_reset_envs: null argument");
+    if (count < 0 || count > s->n) return fail(INV_ERR_INVALID_ARG, "inv_reset_envs: bad count");
+    if (count == 0) return INV_OK;
+    DeviceGuard g(s->cfg.device);
+    Params p = base_params(s);
+    p.idx = idx_dev;
+    p.count = count;
+    CUDA_TRY((launch<OP_RESET, true>(p, s->cfg.obs_dtype, (s->cfg.flags & INV_FLAG_P2_VIEW) != 0, s->sm_count,
+                                     (cudaStream_t)stream)));
+    s->launches += 1;
+    return INV_OK;
+}
+
+int inv_step(inv_sim *s, const int8_t *a1, const int8_t *a2, void *stream)
+{
+    if (!s || !a1) return fail(INV_ERR_INVALID_ARG, "inv_step: null argument");
+    if (!s->was_reset) return fail(INV_ERR_NOT_RESET, "inv_step before inv_reset");
+    if (s->cfg.mode == INV_MODE_SELFPLAY && !a2)
+        return fail(INV_ERR_INVALID_ARG, "opponent_policy required for selfplay mode"); // env_wrappers.py:309
+    DeviceGuard g(s->cfg.device);
+    Params p = base_params(s);
+    p.a1 = a1;
+    p.a2 = a2;
+    CUDA_TRY((launch<OP_STEP, false>(p, s->cfg.obs_dtype, (s->cfg.flags & INV_FLAG_P2_VIEW) != 0, s->sm_count,
+                                     (cudaStream_t)stream)));
+    s->launches += 1;
+    return INV_OK;
+}
+
+static int copy_outputs(inv_sim *s, cudaStream_t st, void *obs_p1, float *extra_p1, void *obs_p2, float *extra_p2,
+                        float *reward, uint8_t *done, uint8_t *info, int32_t *episode_steps, double *episode_return)
+{
+    const int64_t n = s->n;
+    const size_t ob = (size_t)n * INV_OBS_ELEMS * obs_elem_bytes(s->cfg.obs_dtype);
+    if (obs_p1) CUDA_TRY(cudaMemcpyAsync(obs_p1, s->obs1, ob, cudaMemcpyDeviceToHost, st));
+    if (extra_p1) CUDA_TRY(cudaMemcpyAsync(extra_p1, s->extra1, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    if (obs_p2) {
+        if (!s->obs2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
+        CUDA_TRY(cudaMemcpyAsync(obs_p2, s->obs2, ob, cudaMemcpyDeviceToHost, st));
+    }
+    if (extra_p2) {
+        if (!s->extra2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
+        CUDA_TRY(cudaMemcpyAsync(extra_p2, s->extra2, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    }
+    if (reward) CUDA_TRY(cudaMemcpyAsync(reward, s->reward, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (done) CUDA_TRY(cudaMemcpyAsync(done, s->done, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (info) CUDA_TRY(cudaMemcpyAsync(info, s->info, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (episode_steps) CUDA_TRY(cudaMemcpyAsync(episode_steps, s->ep_steps, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (episode_return) CUDA_TRY(cudaMemcpyAsync(episode_return, s->ep_return, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return INV_OK;
+}
+
+int inv_step_host(inv_sim *s, const int8_t *a1, const int8_t *a2, void *obs_p1, float *extra_p1, void *obs_p2,
+                  float *extra_p2, float *reward, uint8_t *done, uint8_t *info, int32_t *episode_steps,
+                  double *episode_return)
+{
+    if (!s || !a1) return fail(INV_ERR_INVALID_ARG, "inv_step_host: null argument");
+    if (!s->was_reset) return fail(INV_ERR_NOT_RESET, "inv_step_host before inv_reset");
+    const bool selfplay = s->cfg.mode == INV_MODE_SELFPLAY;
+    if (selfplay && !a2) return fail(INV_ERR_INVALID_ARG, "opponent_policy required for selfplay mode");
+    const int64_t n = s->n;
+    // discrete_to_action raises before anything is stepped (env_wrappers.py:302, :66)
+    for (int64_t i = 0; i < n; ++i) {
+        if ((uint8_t)a1[i] > 12) return fail(INV_ERR_INVALID_ACTION, "Invalid action_id: must be 0-12");
+        if (selfplay && (uint8_t)a2[i] > 12) return fail(INV_ERR_INVALID_ACTION, "Invalid action_id: must be 0-12");
+    }
+    DeviceGuard g(s->cfg.device);
+    cudaStream_t st = s->host_stream;
+    // action ids travel host -> pinned staging -> device on the handle's own stream
+    memcpy(s->h_a1, a1, (size_t)n);
+    CUDA_TRY(cudaMemcpyAsync(s->d_a1, s->h_a1, (size_t)n, cudaMemcpyHostToDevice, st));
+    if (selfplay) {
+        memcpy(s->h_a2, a2, (size_t)n);
+        CUDA_TRY(cudaMemcpyAsync(s->d_a2, s->h_a2, (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    int rc = inv_step(s, s->d_a1, selfplay ? s->d_a2 : nullptr, st);
+    if (rc != INV_OK) return rc;
+    return copy_outputs(s, st, obs_p1, extra_p1, obs_p2, extra_p2, reward, done, info, episode_steps, episode_return);
+}
+
+int inv_reset_host(inv_sim *s, void *obs_p1, float *extra_p1, void *obs_p2, float *extra_p2)
+{
+    if (!s) return fail(INV_ERR_INVALID_ARG, "inv_reset_host: null handle");
+    DeviceGuard g(s->cfg.device);
+    int rc = inv_reset(s, s->host_stream);
+    if (rc != INV_OK) return rc;
+    return copy_outputs(s, s->host_stream, obs_p1, extra_p1, obs_p2, extra_p2, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int inv_host_alloc(void **out, int64_t nbytes)
+{
+    if (!out || nbytes <= 0) return fail(INV_ERR_INVALID_ARG, "inv_host_alloc: bad argument");
+    CUDA_TRY(cudaMallocHost(out, (size_t)nbytes));
+    return INV_OK;
+}
+
+int inv_host_free(void *p)
+{
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return INV_OK;
+}
+
+int inv_get_buffer(inv_sim *s, int which, void **dev_ptr, int64_t *nbytes)
+{
+    if (!s || !dev_ptr) return fail(INV_ERR_INVALID_ARG, "inv_get_buffer: null argument");
+    const int64_t n = s->n;
+    const int64_t ob = n * INV_OBS_ELEMS * (int64_t)obs_elem_bytes(s->cfg.obs_dtype);
+    void *p = nullptr;
+    int64_t b = 0;
+    switch (which) {
+    case INV_BUF_OBS_P1: p = s->obs1; b = ob; break;
+    case INV_BUF_EXTRA_P1: p = s->extra1; b = n * 16; break;
+    case INV_BUF_OBS_P2: p = s->obs2; b = s->obs2 ? ob : 0; break;
+    case INV_BUF_EXTRA_P2: p = s->extra2; b = s->extra2 ? n * 16 : 0; break;
+    case INV_BUF_REWARD: p = s->reward; b = n * 4; break;
+    case INV_BUF_DONE: p = s->done; b = n; break;
+    case INV_BUF_INFO: p = s->info; b = n; break;
+    case INV_BUF_EPISODE_STEPS: p = s->ep_steps; b = n * 4; break;
+    case INV_BUF_EPISODE_RETURN: p = s->ep_return; b = n * 8; break;
+    case INV_BUF_PACKED_STATE: p = s->state; b = n * INV_PACKED_STATE_BYTES; break;
+    case INV_BUF_DEBUG_RESULT: p = s->dbg; b = n; break;
+    default: return fail(INV_ERR_INVALID_ARG, "inv_get_buffer: unknown buffer id");
+    }
+    if (!p) return fail(INV_ERR_INVALID_ARG, "inv_get_buffer: buffer not allocated for this configuration");
+    *dev_ptr = p;
+    if (nbytes) *nbytes = b;
+    return INV_OK;
+}
+
+int inv_set_draw_table(inv_sim *s, const uint32_t *table_dev)
+{
+    if (!s) return fail(INV_ERR_INVALID_ARG, "inv_set_draw_table: null handle");
+    s->table = table_dev;
+    return INV_OK;
+}
+
+int inv_export_state(inv_sim *s, inv_env_state *out, int64_t first, int64_t count)
+{
+    if (!s || !out) return fail(INV_ERR_INVALID_ARG, "inv_export_state: null argument");
+    if (first < 0 || count < 0 || first + count > s->n) return fail(INV_ERR_INVALID_ARG, "inv_export_state: bad range");
+    if (count == 0) return INV_OK;
+    DeviceGuard g(s->cfg.device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<uint32_t> buf((size_t)count * 20);
+    const uint32_t *pl[5];
+    for (int k = 0; k < 5; ++k) {
+        uint32_t *dst = buf.data() + (size_t)k * count * 4;
+        CUDA_TRY(cudaMemcpy(dst, reinterpret_cast<const char *>(s->state) + ((size_t)k * s->n + first) * 16,
+                            (size_t)count * 16, cudaMemcpyDeviceToHost));
+        pl[k] = dst;
+    }
+    for (int64_t i = 0; i < count; ++i) unpack_host(pl, i, &out[i]);
+    return INV_OK;
+}
+
+int inv_import_state(inv_sim *s, const inv_env_state *in, int64_t first, int64_t count)
+{
+    if (!s || !in) return fail(INV_ERR_INVALID_ARG, "inv_import_state: null argument");
+    if (first < 0 || count < 0 || first + count > s->n) return fail(INV_ERR_INVALID_ARG, "inv_import_state: bad range");
+    if (count == 0) return INV_OK;
+    DeviceGuard g(s->cfg.device);
+    std::vector<uint32_t> buf((size_t)count * 20);
+    uint32_t *pl[5];
+    for (int k = 0; k < 5; ++k) pl[k] = buf.data() + (size_t)k * count * 4;
+    for (int64_t i = 0; i < count; ++i)
+        if (!pack_host(&in[i], pl, i)) return fail(INV_ERR_INVALID_ARG, "inv_import_state: field out of range");
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int k = 0; k < 5; ++k)
+        CUDA_TRY(cudaMemcpy(reinterpret_cast<char *>(s->state) + ((size_t)k * s->n + first) * 16, pl[k],
+                            (size_t)count * 16, cudaMemcpyHostToDevice));
+    s->was_reset = true;
+    return INV_OK;
+}
+
+int inv_obs_from_packed(inv_sim *s, const void *packed_dev, int64_t stride, int64_t count, int view, int obs_dtype,
+                        void *obs_out, float *extra_out, void *stream)
+{
+    if (!s || !packed_dev || !obs_out || !extra_out) return fail(INV_ERR_INVALID_ARG, "inv_obs_from_packed: null argument");
+    if (count < 0 || stride < count || (view != 0 && view != 1)) return fail(INV_ERR_INVALID_ARG, "inv_obs_from_packed: bad argument");
+    if (count == 0) return INV_OK;
+    DeviceGuard g(s->cfg.device);
+    Params p = base_params(s);
+    p.state_in = static_cast<const uint4 *>(packed_dev);
+    p.stride = stride;
+    p.count = count;
+    p.view = view;
+    p.obs1 = obs_out;
+    p.extra1 = extra_out;
+    p.table = nullptr;
+    cudaError_t ce;
+    switch (obs_dtype) {
+    case INV_OBS_F32: ce = launch_e<OP_OBS, INV_OBS_F32, false, false>(p, s->sm_count, (cudaStream_t)stream); break;
+    case INV_OBS_BF16: ce = launch_e<OP_OBS, INV_OBS_BF16, false, false>(p, s->sm_count, (cudaStream_t)stream); break;
+    case INV_OBS_U8: ce = launch_e<OP_OBS, INV_OBS_U8, false, false>(p, s->sm_count, (cudaStream_t)stream); break;
+    default: return fail(INV_ERR_INVALID_ARG, "inv_obs_from_packed: unknown obs_dtype");
+    }
+    CUDA_TRY(ce);
+    s->launches += 1;
+    return INV_OK;
+}
+
+int inv_debug_phase(inv_sim *s, int phase, int pid, int arg, int arg2, void *stream)
+{
+    if (!s) return fail(INV_ERR_INVALID_ARG, "inv_debug_phase: null handle");
+    if (phase < 0 || phase > INV_PHASE_DUMMY_POLICY || (pid != 0 && pid != 1))
+        return fail(INV_ERR_INVALID_ARG, "inv_debug_phase: bad phase or pid");
+    if ((phase <= INV_PHASE_WIDE_SHOT) && (arg < 0 || arg > 3)) return fail(INV_ERR_INVALID_ARG, "inv_debug_phase: bad direction");
+    if (phase == INV_PHASE_STEP_PLAYERS && (arg < 0 || arg > 12 || arg2 < 0 || arg2 > 12))
+        return fail(INV_ERR_INVALID_ACTION, "Invalid action_id: must be 0-12");
+    DeviceGuard g(s->cfg.device);
+    Params p = base_params(s);
+    p.phase = phase; p.pid = pid; p.arg = arg; p.arg2 = arg2;
+    CUDA_TRY((launch_one<OP_DEBUG, INV_OBS_F32, false, false, 32>(p, s->sm_count, (cudaStream_t)stream)));
+    s->launches += 1;
+    return INV_OK;
+}
+
+int inv_poll_status(inv_sim *s, void *stream, uint32_t *bits)
+{
+    if (!s || !bits) return fail(INV_ERR_INVALID_ARG, "inv_poll_status: null argument");
+    DeviceGuard g(s->cfg.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(s->h_status, s->status, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemsetAsync(s->status, 0, 4, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *bits = *s->h_status;
+    return INV_OK;
+}
+
+int64_t inv_launch_count(const inv_sim *s) { return s ? s->launches : 0; }
+
+} // extern "C"

@@ -51,3 +51,49 @@ class OracleBackend:
             L.orc_build_obs(C.byref(b.envs[i]), 0, b.obs1[i].ctypes.data, b.extra1[i].ctypes.data)
             L.orc_build_obs(C.byref(b.envs[i]), 1, o2[i].ctypes.data, e2[i].ctypes.data)
         return b.obs1, b.extra1, o2, e2
+
+
+class CudaBackend:
+    """The CUDA product (through BatchedInversus -> C ABI) as a scenario backend."""
+
+    def __init__(self, sc, env_id_base=0, n=None, obs_dtype="f32"):
+        import torch
+        from inversus_b200 import BatchedInversus
+        self.torch = torch
+        self.selfplay = sc["mode"] == "selfplay"
+        self.sim = BatchedInversus(n or sc["n"], sc["mode"], sc["difficulty"], sc["max_steps"], seed=sc["seed"],
+                                   auto_reset=(sc["resets"] == "auto"), env_id_base=env_id_base,
+                                   obs_dtype=obs_dtype, p2_view=True)
+
+    def _table(self, table):
+        self.sim.set_draw_table(table)
+
+    def reset(self, table):
+        self._table(table)
+        self.sim.reset()
+
+    def step(self, a1, a2, table, auto_reset):
+        assert auto_reset == self.sim.auto_reset
+        self._table(table)
+        s = self.sim
+        s.step(self.torch.from_numpy(np.asarray(a1, np.int8)).cuda(),
+               None if a2 is None else self.torch.from_numpy(np.asarray(a2, np.int8)).cuda())
+        out = dict(reward=s.reward.cpu().numpy(), done=s.done.cpu().numpy(), flags=s.info.cpu().numpy(),
+                   episode_steps=s.episode_steps.cpu().numpy(), episode_return=s.episode_return.cpu().numpy(),
+                   obs1=s.obs.float().cpu().numpy(), extra1=s.extra.cpu().numpy())
+        if self.selfplay:
+            out["obs2"], out["extra2"] = s.obs_p2.float().cpu().numpy(), s.extra_p2.cpu().numpy()
+        assert s.poll_status() == 0
+        return out
+
+    def reset_envs(self, idx, table):
+        self._table(table)
+        self.sim.reset_envs(np.asarray(idx, np.int64))
+
+    def state(self):
+        return self.sim.export_state()
+
+    def obs(self):
+        s = self.sim
+        return (s.obs.float().cpu().numpy(), s.extra.cpu().numpy(),
+                s.obs_p2.float().cpu().numpy(), s.extra_p2.cpu().numpy())

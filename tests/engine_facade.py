@@ -152,3 +152,142 @@ class OracleEngine:
         x = np.zeros(4, np.float32)
         self.L.orc_build_obs(C.byref(self.e), viewer, g.ctypes.data, x.ctypes.data)
         return g, x
+
+
+class CudaEngine:
+    """The CUDA product behind core.py's method names: each call runs ONE engine method on the
+    device through inv_debug_phase (the same __device__ functions the fused step kernel inlines).
+    Fixed 15x10 board; field pokes go through inv_export_state / inv_import_state."""
+
+    def __init__(self, width=15, height=10, seed=1234):
+        from inversus_b200 import BatchedInversus, _capi
+        assert width <= 15 and height <= 10
+        self.capi = _capi
+        self.sim = BatchedInversus(1, "selfplay", "hard", 500, seed=seed, auto_reset=False)
+        self.width, self.height = 15, 10
+        self.player_color = BLACK
+        self.sim.reset()
+        self._pull()
+
+    def _pull(self):
+        self._st = self.sim.export_state()
+        self._dirty = False
+
+    def _push(self):
+        if self._dirty:
+            self.sim.import_state(self._st)
+            self._dirty = False
+
+    def _call(self, phase, pid=0, arg=0, arg2=0):
+        self._push()
+        res = int(self.sim.debug_phase(phase, pid, arg, arg2).cpu()[0])
+        assert self.sim.poll_status() == 0
+        self._pull()
+        return res
+
+    def _pv(self, name):
+        idx = {"x": 0, "y": 1, "ammo": 2, "reload_counter": 3, "alive": 4}
+
+        def get(k):
+            return int(self._st[name][0][idx[k]])
+
+        def set_(k, v):
+            self._st[name][0][idx[k]] = v
+            self._dirty = True
+        return _PlayerView(get, set_)
+
+    @property
+    def player1(self):
+        return self._pv("p1")
+
+    @property
+    def player2(self):
+        return self._pv("p2")
+
+    @property
+    def player_x(self):
+        return int(self._st["p1"][0][0])
+
+    @player_x.setter
+    def player_x(self, v):
+        self._st["p1"][0][0] = v
+        self._dirty = True
+
+    @property
+    def player_y(self):
+        return int(self._st["p1"][0][1])
+
+    @player_y.setter
+    def player_y(self, v):
+        self._st["p1"][0][1] = v
+        self._st["n_bullets"][0] = 0  # core.py:180-181
+        self._dirty = True
+
+    @property
+    def bullets(self):
+        n = int(self._st["n_bullets"][0])
+        return [Bullet(*(int(v) for v in self._st["bullets"][0][i])) for i in range(n)]
+
+    @bullets.setter
+    def bullets(self, lst):
+        self._st["n_bullets"][0] = len(lst)
+        self._st["bullets"][0][:] = 0
+        for i, b in enumerate(lst):
+            self._st["bullets"][0][i] = (b.x, b.y, b.dir, b.owner)
+        self._dirty = True
+
+    def get_bullets(self):
+        return self.bullets
+
+    def _get_tile(self, x, y):
+        if not (0 <= x < self.width and 0 <= y < self.height):
+            raise IndexError
+        i = y * 15 + x
+        return int(self._st["tiles"][0][i >> 5] >> (i & 31)) & 1
+
+    def _set_tile(self, x, y, c):
+        if not (0 <= x < self.width and 0 <= y < self.height):
+            raise IndexError
+        i = y * 15 + x
+        w = int(self._st["tiles"][0][i >> 5])
+        w = (w | (1 << (i & 31))) if c else (w & ~(1 << (i & 31)))
+        self._st["tiles"][0][i >> 5] = w
+        self._dirty = True
+
+    def reset(self):
+        self._call(self.capi.PHASE_ENGINE_RESET)
+
+    def try_move_player(self, d, pid=P1):
+        return bool(self._call(self.capi.PHASE_TRY_MOVE, pid, d))
+
+    def spawn_bullet(self, d, pid=P1):
+        return bool(self._call(self.capi.PHASE_SPAWN_BULLET, pid, d))
+
+    def spawn_wide_shot(self, pid, d):
+        return bool(self._call(self.capi.PHASE_WIDE_SHOT, pid, d))
+
+    def _reload_ammo(self):
+        self._call(self.capi.PHASE_RELOAD)
+
+    def update_bullets(self):
+        self._call(self.capi.PHASE_UPDATE_BULLETS)
+
+    def step_players(self, a1, a2):
+        self._call(self.capi.PHASE_STEP_PLAYERS, 0, a1, a2)
+
+    def step(self, a1):
+        self.step_players(a1, NONE)
+
+    def is_round_over(self):
+        return not (self.player1.alive and self.player2.alive)
+
+    def get_winner(self):
+        a1, a2 = self.player1.alive, self.player2.alive
+        if a1 and a2:
+            return None
+        return P2 if (a2 and not a1) else (P1 if (a1 and not a2) else None)
+
+    def observation(self, viewer=P1):
+        self._push()
+        g, e = self.sim.obs_from_packed(self.sim.snapshot(), view=viewer, obs_dtype="f32")
+        return g[0].cpu().numpy(), e[0].cpu().numpy()

@@ -1,0 +1,86 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds/loads without a GPU, exports every
+symbol include/inversus_b200.h declares, the ctypes mirror matches the header's layout constants,
+and -- with no device present -- every compute entry point fails loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "inversus_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(inv_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from inversus_b200 import _capi, build_library
+    path = build_library()
+    assert os.path.exists(path)
+    lib = C.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(_capi.SYMBOLS) == declared, "ctypes binding and header drifted apart"
+    assert _capi.load().inv_abi_version() == 1
+
+
+def test_header_constants_match_the_python_mirror():
+    from inversus_b200 import constants as K
+    src = open(HEADER).read()
+
+    def define(name):
+        m = re.search(rf"#define {name}\s+\(?([0-9xA-Fa-fu]+)", src)
+        assert m, name
+        return int(m.group(1).rstrip("u"), 0)
+    assert define("INV_BOARD_W") == K.BOARD_W and define("INV_BOARD_H") == K.BOARD_H
+    assert define("INV_MAX_BULLETS") == K.MAX_BULLETS
+    assert define("INV_PACKED_STATE_BYTES") == K.PACKED_STATE_BYTES
+    assert define("INV_TABLE_STRIDE") == K.TABLE_STRIDE and define("INV_TABLE_RESET_OFF") == K.TABLE_RESET_OFF
+    assert define("INV_STREAM_RESET") == K.STREAM_RESET
+    assert K.OBS_ELEMS == 1800
+    assert K.algorithmic_bytes_per_env_step(4, False) == 7200 + 16 + 18 + 160 + 1
+
+
+def test_state_struct_layout_matches_oracle_and_harness():
+    from inversus_b200 import _capi
+    from oracle import oracle as orc
+    import ref_harness
+    assert _capi.STATE_DTYPE == orc.STATE_DTYPE == ref_harness.STATE_DTYPE
+    assert _capi.STATE_DTYPE.itemsize == 144
+
+
+def test_kernel_thresholds_in_the_cuda_source_match_constants():
+    from inversus_b200 import constants as K
+    cu = open(os.path.join(ROOT, "inversus-reinforcement-learning_b200", "csrc", "inversus_kernels.cuh")).read()
+    for name, val in (("kThreshShootHard", K.THRESH_SHOOT_HARD), ("kThreshRandMoveHard", K.THRESH_RANDMOVE_HARD),
+                      ("kThreshMoveEasy", K.THRESH_MOVE_EASY)):
+        m = re.search(rf"{name}\s*=\s*(\d+)u", cu)
+        assert m and int(m.group(1)) == val, name
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from inversus_b200 import BatchedInversus, InversusError, MultiEnvRunner
+    with pytest.raises(InversusError, match="no CPU fallback"):
+        BatchedInversus(4, seed=0)
+    with pytest.raises(InversusError):
+        MultiEnvRunner(4, seed=0)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the package may reference it."""
+    pkg = os.path.join(ROOT, "inversus-reinforcement-learning_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("the oracle and the live-reference harness", ""), f

@@ -1,0 +1,159 @@
+"""GPU parity tests proper: the CUDA product, called through the C ABI, against
+  (a) the committed golden fixtures = outputs of the live Python reference, and
+  (b) the CPU oracle on fresh seeded inputs at sizes the oracle finishes in seconds.
+Bar (BASELINE.json north_star): bit-exact integer state, bullets (ordered), done, info flags and
+observations; float rewards within 1e-6 relative -- in fact asserted bit-exact in float32, and the
+running fp64 episode return bit-exact too.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from golden.scenarios import SCENARIOS, compare, run_scenario
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_cuda_reproduces_reference_fixture(name):
+    from backends import CudaBackend
+    sc = SCENARIOS[name]
+    gold = dict(np.load(os.path.join(GOLD, f"{name}.npz")))
+    rec = run_scenario(CudaBackend(sc), sc)
+    compare(rec, gold, float_rtol=1e-6, what=name)
+    assert np.array_equal(rec["reward_f32"], gold["reward_f32"])
+    assert np.array_equal(rec["episode_return"], gold["episode_return"])
+
+
+FRESH = {
+    "gpu_hard": dict(mode="dummy", difficulty="hard", max_steps=500, n=4096, T=600, seed=201, actions="uniform", draws="philox", resets="auto"),
+    "gpu_easy": dict(mode="dummy", difficulty="easy", max_steps=120, n=2048, T=300, seed=202, actions="shooty", draws="philox", resets="auto"),
+    "gpu_selfplay": dict(mode="selfplay", difficulty="hard", max_steps=200, n=2048, T=300, seed=203, actions="shooty", draws="philox", resets="auto"),
+    "gpu_charge": dict(mode="dummy", difficulty="hard", max_steps=500, n=3000, T=250, seed=204, actions="charge", draws="philox", resets="auto"),
+    "gpu_table": dict(mode="dummy", difficulty="hard", max_steps=90, n=1000, T=200, seed=205, actions="passive", draws="table", resets="manual"),
+    "gpu_ragged": dict(mode="selfplay", difficulty="hard", max_steps=50, n=131, T=120, seed=206, actions="uniform", draws="philox", resets="manual"),
+    "gpu_one": dict(mode="dummy", difficulty="hard", max_steps=30, n=1, T=100, seed=207, actions="uniform", draws="philox", resets="auto"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FRESH))
+def test_cuda_matches_oracle_on_fresh_seeds(name):
+    """Differential test vs the oracle, every step, every env, every observable (incl. all 1800
+    observation elements of both views). Sizes include ragged tiles (131, 3000, 1) and > 1 tile."""
+    from backends import CudaBackend, OracleBackend
+    sc = FRESH[name]
+    want = run_scenario(OracleBackend(sc, nthreads=8), sc)
+    got = run_scenario(CudaBackend(sc), sc)
+    compare(got, want, float_rtol=1e-6, what=name)
+    assert np.array_equal(got["reward_f32"], want["reward_f32"])
+    assert np.array_equal(got["episode_return"], want["episode_return"])
+
+
+def test_results_do_not_depend_on_the_shard_count():
+    """Envs [0,N) on one handle == two handles owning [0,N/2) and [N/2,N) (env_id_base): the
+    multi-GPU layout of DESIGN.md with no collective in the step path."""
+    import torch
+    from inversus_b200 import BatchedInversus
+    from inversus_b200.sharding import shard_range
+    n, T = 1000, 80
+    rs = np.random.RandomState(5)
+    acts = rs.randint(0, 13, size=(T, n)).astype(np.int8)
+    whole = BatchedInversus(n, "dummy", "hard", 60, seed=9)
+    parts = []
+    for r in range(3):
+        first, count = shard_range(n, r, 3)
+        parts.append((first, count, BatchedInversus(count, "dummy", "hard", 60, seed=9, env_id_base=first)))
+    whole.reset()
+    for _, _, p in parts:
+        p.reset()
+    for t in range(T):
+        whole.step(torch.from_numpy(acts[t]).cuda())
+        for first, count, p in parts:
+            p.step(torch.from_numpy(acts[t, first:first + count]).cuda())
+    ws = whole.export_state()
+    for first, count, p in parts:
+        ps = p.export_state()
+        for f in ws.dtype.names:
+            assert np.array_equal(ws[f][first:first + count], ps[f]), f
+        assert torch.equal(whole.obs[first:first + count], p.obs)
+        assert torch.equal(whole.reward[first:first + count], p.reward)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "u8"])
+def test_narrow_observation_dtypes_are_lossless(dtype):
+    """bf16 / u8 observation planes carry exactly the f32 values (all are 0 or 1)."""
+    import torch
+    from inversus_b200 import BatchedInversus
+    n, T = 777, 40
+    rs = np.random.RandomState(3)
+    a = BatchedInversus(n, "selfplay", "hard", 30, seed=4, obs_dtype="f32")
+    b = BatchedInversus(n, "selfplay", "hard", 30, seed=4, obs_dtype=dtype)
+    a.reset(), b.reset()
+    assert torch.equal(a.obs, b.obs.float())
+    for _ in range(T):
+        a1 = torch.from_numpy(rs.randint(0, 13, n).astype(np.int8)).cuda()
+        a2 = torch.from_numpy(rs.randint(5, 13, n).astype(np.int8)).cuda()
+        a.step(a1, a2), b.step(a1, a2)
+        assert torch.equal(a.obs, b.obs.float())
+        assert torch.equal(a.obs_p2, b.obs_p2.float())
+        assert torch.equal(a.extra, b.extra) and torch.equal(a.reward, b.reward)
+
+
+def test_obs_from_packed_snapshots_matches_live_observations():
+    """K3: observations rebuilt from 80-byte packed-state snapshots == the observations the step
+    kernel wrote, for both views and all three dtypes."""
+    import torch
+    from inversus_b200 import BatchedInversus
+    n = 1500
+    rs = np.random.RandomState(8)
+    s = BatchedInversus(n, "selfplay", "hard", 40, seed=6)
+    s.reset()
+    for _ in range(25):
+        s.step(torch.from_numpy(rs.randint(0, 13, n).astype(np.int8)).cuda(),
+               torch.from_numpy(rs.randint(0, 13, n).astype(np.int8)).cuda())
+    snap = s.snapshot()
+    for view, (g, e) in enumerate(((s.obs, s.extra), (s.obs_p2, s.extra_p2))):
+        for dt in ("f32", "bf16", "u8"):
+            og, oe = s.obs_from_packed(snap, view=view, obs_dtype=dt)
+            assert torch.equal(og.float(), g) and torch.equal(oe, e)
+    # a sub-range of a larger snapshot buffer (count < stride)
+    og, oe = s.obs_from_packed(snap, view=0, count=100)
+    assert torch.equal(og, s.obs[:100]) and torch.equal(oe, s.extra[:100])
+
+
+def test_invalid_action_ids_are_rejected_not_ignored():
+    import torch
+    from inversus_b200 import BatchedInversus, MultiEnvRunner
+    from inversus_b200.constants import STATUS_INVALID_ACTION
+    r = MultiEnvRunner(4, "dummy", "hard", 500, seed=0)
+    r.reset()
+    before = r.sim.export_state()
+    with pytest.raises(ValueError, match="Invalid action_id"):  # env_wrappers.py:66
+        r.step(np.array([0, 13, 1, 2]))
+    with pytest.raises(ValueError, match="Invalid action_id"):
+        r.step(np.array([0, -1, 1, 2]))
+    after = r.sim.export_state()
+    assert all(np.array_equal(before[f], after[f]) for f in before.dtype.names)  # nothing was stepped
+    s = BatchedInversus(64, "dummy", "hard", 500, seed=0)
+    s.reset()
+    bad = torch.zeros(64, dtype=torch.int8, device="cuda")
+    bad[5] = 13
+    s.step(bad)
+    assert s.poll_status() & STATUS_INVALID_ACTION
+    assert s.poll_status() == 0  # sticky bit is cleared by the poll
+    with pytest.raises(ValueError):
+        BatchedInversus(4, "nonsense")  # env_wrappers.py:316
+    sp = BatchedInversus(4, "selfplay", seed=0)
+    sp.reset()
+    with pytest.raises(ValueError, match="opponent_policy required"):  # env_wrappers.py:309
+        sp.step(torch.zeros(4, dtype=torch.int8, device="cuda"))
+
+
+def test_step_before_reset_fails_loudly():
+    import torch
+    from inversus_b200 import BatchedInversus, InversusError
+    s = BatchedInversus(8, seed=0)
+    with pytest.raises(InversusError):
+        s.step(torch.zeros(8, dtype=torch.int8, device="cuda"))
