@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the rollout hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on host cores
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "cfg 2"): random-action step throughput,
+vs_dummy / hard difficulty, max_episode_steps=500, `--envs-per-gpu` envs per GPU (default
+1 048 576), fp32 observations as the reference API specifies, auto-reset on done. A "step" is one
+fused step+obs kernel launch over the whole batch. P1 action ids are pre-generated uniformly on
+0..12 (16 int8 arrays resident in HBM, cycled); synthetic data, no dataset involved.
+
+Prints ONE JSON line (rank 0). Keys: see the task contract; `roofline` = fused step kernel vs the
+measured HBM copy peak; `cpu_baseline` = the oracle port timed on this box's host cores;
+`e2e` = the same metric through the host-buffer C-ABI call (inv_step_host) with the action upload
+and the full observation/reward/done download inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+N_ACTION_SETS = 16
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--obs-dtype", choices=["f32", "bf16", "u8"], default="f32")
+    ap.add_argument("--mode", choices=["dummy", "selfplay"], default="dummy")
+    ap.add_argument("--difficulty", choices=["easy", "hard"], default="hard")
+    ap.add_argument("--max-episode-steps", type=int, default=500)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=4, help="timed host-buffer steps (0 = skip e2e)")
+    ap.add_argument("--e2e-envs", type=int, default=0, help="envs per GPU for the e2e leg (0 = same as --envs-per-gpu)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--cpu-sample-envs", type=int, default=65536)
+    ap.add_argument("--sweep", action="store_true", help="also time 4K..4M envs (written to stderr)")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic(obs_dtype, mode, n_envs):
+    """dram bytes per launch from the committed ncu capture of this kernel (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get(f"{mode}_{obs_dtype}") if t.get("envs") == n_envs else None
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, v in names.items():
+                    if bits & v:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU leg: the oracle port (oracle/inversus_oracle.c) on the host cores. Used as `cpu_baseline` of
+# our own line and as the whole measurement of `--impl reference`. The reference itself is pure
+# Python and cannot travel to the GPU box; SURVEY.md section 6 gives its own speed measured in the
+# builder container (about 5e3 env-steps/s per core through MultiEnvRunner.step).
+def run_oracle(args, n_envs, steps, warmup, budget_s=None):
+    import numpy as np
+    from oracle import oracle as orc
+    cores = orc.lib().orc_max_threads()
+    b = orc.OracleBatch(n_envs, args.mode, args.difficulty, args.max_episode_steps, seed=args.seed, nthreads=cores)
+    rs = np.random.RandomState(args.seed)
+    acts = rs.randint(0, 13, size=(N_ACTION_SETS, n_envs)).astype(np.int8)
+    acts2 = rs.randint(0, 13, size=(N_ACTION_SETS, n_envs)).astype(np.int8) if args.mode == "selfplay" else None
+    b.reset()
+
+    def one(t):
+        b.step(acts[t % N_ACTION_SETS], None if acts2 is None else acts2[t % N_ACTION_SETS], auto_reset=True)
+    for t in range(warmup):
+        one(t)
+    done_steps = 0
+    t0 = time.perf_counter()
+    for t in range(steps):
+        one(warmup + t)
+        done_steps += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n_envs * done_steps / dt, "seconds": dt, "steps": done_steps, "cores": cores}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    n = args.cpu_sample_envs
+    r = run_oracle(args, n, args.steps, max(args.warmup, 3), budget_s=150.0)  # bounded: ends within minutes
+    sample = (f"{n} envs (global ids 0..{n - 1} of the {args.envs_per_gpu}-env workload) x {r['steps']} steps, "
+              f"fp32 obs written every step, auto-reset, {r['cores']} pthreads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * r["seconds"] / max(r["steps"], 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is pure Python (cannot travel to the GPU box); this is its algorithm restated in C "
+                "(oracle/inversus_oracle.c) on all host cores. Python reference measured in the builder "
+                "container: ~5e3 env-steps/s per core (SURVEY.md section 6).",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"random-action fused step+obs, vs_{args.mode} {args.difficulty}, "
+                    f"{args.envs_per_gpu} envs/GPU, max_episode_steps={args.max_episode_steps} "
+                    f"(BASELINE.json configs[1])",
+        "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
+        "mode": args.mode, "difficulty": args.difficulty, "max_episode_steps": args.max_episode_steps,
+        "obs_dtype": args.obs_dtype, "auto_reset": True,
+        "actions": f"pre-generated uniform int8 ids, {N_ACTION_SETS} arrays in HBM cycled",
+        "parallelism": f"env-sharded x{world}, no collective in the step path",
+        "l2": "per-step working set (obs write stream, 7.2 KB/env) far exceeds the 126 MB L2; no explicit flush",
+    }
+
+
+def time_steps(sim, torch, acts, acts2, steps, first_t=0):
+    """K back-to-back launches; returns per-launch ms measured with CUDA events on the launch stream."""
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for t in range(steps):
+        k = (first_t + t) % N_ACTION_SETS
+        sim.step(acts[k], None if acts2 is None else acts2[k])
+        ev[t + 1].record()
+    torch.cuda.synchronize()
+    return [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)], ev[0].elapsed_time(ev[steps])
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from inversus_b200 import BatchedInversus, constants
+    from inversus_b200.sharding import dist_env
+
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:  # convenience: relaunch under torchrun
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", local_rank if world > 1 else 0)
+    n = args.envs_per_gpu
+    selfplay = args.mode == "selfplay"
+
+    sim = BatchedInversus(n, args.mode, args.difficulty, args.max_episode_steps, seed=args.seed,
+                          device=dev.index, obs_dtype=args.obs_dtype, auto_reset=True, env_id_base=rank * n)
+    g = torch.Generator(device=dev)
+    g.manual_seed(args.seed * 1000 + rank)
+    acts = [torch.randint(0, 13, (n,), device=dev, dtype=torch.int8, generator=g) for _ in range(N_ACTION_SETS)]
+    acts2 = [torch.randint(0, 13, (n,), device=dev, dtype=torch.int8, generator=g) for _ in range(N_ACTION_SETS)] if selfplay else None
+    sim.reset()
+    W = max(args.warmup, 3)
+    for t in range(W):
+        sim.step(acts[t % N_ACTION_SETS], None if acts2 is None else acts2[t % N_ACTION_SETS])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ timed region (device)
+    launches0 = sim.launch_count
+    barrier()
+    with ClockSampler(dev.index) as clk:
+        per_launch_ms, total_ms = time_steps(sim, torch, acts, acts2, args.steps, W)
+        barrier()
+    launches = sim.launch_count - launches0
+    status = sim.poll_status()
+    assert status == 0, f"device status bits {status}"
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = n * world * args.steps / (total_ms_max * 1e-3)
+
+    elem = {"f32": 4, "bf16": 2, "u8": 1}[args.obs_dtype]
+    alg_bytes = constants.algorithmic_bytes_per_env_step(elem, selfplay) * n
+    avg_launch_ms = sum(per_launch_ms) / len(per_launch_ms)
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (avg_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": recorded_traffic(args.obs_dtype, args.mode, n),
+                "kernel": "inv::inv_kernel<OP_STEP> (fused step+obs)", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "algorithmic_bytes_per_env_step": alg_bytes // n,
+                "avg_launch_ms": avg_launch_ms, "min_launch_ms": min(per_launch_ms),
+                "median_launch_ms": statistics.median(per_launch_ms)}
+
+    # ------------------------------------------------------------------ e2e: host buffers through inv_step_host
+    e2e = None
+    if args.e2e_steps > 0:
+        ne = args.e2e_envs or n
+        esim = sim if ne == n else BatchedInversus(ne, args.mode, args.difficulty, args.max_episode_steps,
+                                                   seed=args.seed, device=dev.index, obs_dtype=args.obs_dtype,
+                                                   auto_reset=True, env_id_base=rank * ne)
+        if esim is not sim:
+            esim.reset()
+        out = esim.host_buffers(pinned=True)
+        rs = np.random.RandomState(args.seed + rank)
+        h_acts = [rs.randint(0, 13, size=ne).astype(np.int8) for _ in range(4)]
+        h_acts2 = [rs.randint(0, 13, size=ne).astype(np.int8) for _ in range(4)] if selfplay else None
+        for k in range(2):
+            esim.step_host(h_acts[k], None if h_acts2 is None else h_acts2[k], out)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.e2e_steps):
+            esim.step_host(h_acts[k % 4], None if h_acts2 is None else h_acts2[k % 4], out)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        views = 2 if selfplay else 1
+        d2h = ne * (views * (1800 * elem + 16) + 4 + 1 + 1 + 4 + 8)
+        e2e = {"value": ne * world * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": ne * views,
+               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "envs_per_gpu": ne,
+               "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "api": "inv_step_host (C ABI): int8 action ids up, obs+extra+reward+done+info+episode stats down, pinned host buffers",
+               "d2h_gbs": d2h * args.e2e_steps / dt / 1e9}
+
+    # ------------------------------------------------------------------ optional sweep (stderr)
+    if args.sweep and rank == 0:
+        for ns in (4096, 16384, 65536, 262144, 1048576, 4194304):
+            s2 = BatchedInversus(ns, args.mode, args.difficulty, args.max_episode_steps, seed=args.seed,
+                                 device=dev.index, obs_dtype=args.obs_dtype, auto_reset=True)
+            a = [torch.randint(0, 13, (ns,), device=dev, dtype=torch.int8, generator=g) for _ in range(N_ACTION_SETS)]
+            a2 = [torch.randint(0, 13, (ns,), device=dev, dtype=torch.int8, generator=g) for _ in range(N_ACTION_SETS)] if selfplay else None
+            s2.reset()
+            for t2 in range(50):
+                s2.step(a[t2 % N_ACTION_SETS], None if a2 is None else a2[t2 % N_ACTION_SETS])
+            torch.cuda.synchronize()
+            pl, tot = time_steps(s2, torch, a, a2, 200)
+            bts = constants.algorithmic_bytes_per_env_step(elem, selfplay) * ns
+            print(json.dumps({"sweep_envs": ns, "env_steps_per_sec": ns * 200 / (tot * 1e-3),
+                              "ms_per_step": tot / 200, "hbm_gbs": bts / (tot / 200 * 1e-3) / 1e9,
+                              "frac_of_peak": bts / (tot / 200 * 1e-3) / 1e9 / peak}), file=sys.stderr, flush=True)
+            s2.close()
+            del s2, a, a2
+
+    # ------------------------------------------------------------------ cpu baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_seconds > 0:
+        nc = args.cpu_sample_envs
+        r = run_oracle(args, nc, 10 ** 9, 3, budget_s=args.cpu_seconds)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": f"{nc} envs x {r['steps']} steps ({r['seconds']:.1f} s) of the same workload through "
+                         f"oracle/inversus_oracle.c, fp32 obs written every step, {r['cores']} pthreads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(args, world),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clk.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
