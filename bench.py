@@ -284,6 +284,7 @@ def main():
 
     # ------------------------------------------------------------------ e2e: host buffers through inv_step_host
     e2e = None
+    e2e_variants = None
     if args.e2e_steps > 0:
         ne = args.e2e_envs or n
         esim = sim if ne == n else BatchedInversus(ne, args.mode, args.difficulty, args.max_episode_steps,
@@ -295,25 +296,48 @@ def main():
         rs = np.random.RandomState(args.seed + rank)
         h_acts = [rs.randint(0, 13, size=ne).astype(np.int8) for _ in range(4)]
         h_acts2 = [rs.randint(0, 13, size=ne).astype(np.int8) for _ in range(4)] if selfplay else None
-        for k in range(2):
-            esim.step_host(h_acts[k], None if h_acts2 is None else h_acts2[k], out)
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(args.e2e_steps):
-            esim.step_host(h_acts[k % 4], None if h_acts2 is None else h_acts2[k % 4], out)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
         views = 2 if selfplay else 1
-        d2h = ne * (views * (1800 * elem + 16) + 4 + 1 + 1 + 4 + 8)
-        e2e = {"value": ne * world * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": ne * views,
-               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "envs_per_gpu": ne,
-               "ms_per_step": 1e3 * dt / args.e2e_steps,
-               "api": "inv_step_host (C ABI): int8 action ids up, obs+extra+reward+done+info+episode stats down, pinned host buffers",
-               "d2h_gbs": d2h * args.e2e_steps / dt / 1e9}
+        small = 4 + 1 + 1 + 4 + 8 + views * 16
+
+        def run_e2e(nthreads, frac, with_obs, warm):
+            esim.set_host_path(nthreads, frac)
+            o = out if with_obs else {k: v for k, v in out.items() if not k.startswith("obs")}
+            for k in range(warm):
+                esim.step_host(h_acts[k % 4], None if h_acts2 is None else h_acts2[k % 4], o)
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(args.e2e_steps):
+                esim.step_host(h_acts[k % 4], None if h_acts2 is None else h_acts2[k % 4], o)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            hp = esim.host_path()
+            if not with_obs:
+                d2h = ne * small
+            elif nthreads == 0 or args.obs_dtype != "f32" or ne < 4096:
+                d2h = ne * (views * 1800 * elem + small)
+            else:
+                d2h = ne * small + views * (ne * 256 + int(hp["dma_fraction"] * ne) * 7200)
+            return {"value": ne * world * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": ne * views,
+                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "envs_per_gpu": ne,
+                    "ms_per_step": 1e3 * dt / args.e2e_steps, "host_threads": hp["threads"],
+                    "dma_fraction": round(hp["dma_fraction"], 4)}
+
+        # headline: every output of MultiEnvRunner.step, fp32 observations included, lands in host
+        # buffers. Packed rows cross PCIe and are expanded on the host threads while the copy engine
+        # moves the rest directly (inv_set_host_path, auto-balanced).
+        e2e = run_e2e(None, -1.0, True, warm=6)
+        e2e["api"] = ("inv_step_host (C ABI), pinned host buffers: int8 action ids up; fp32 obs + extra + reward + done + "
+                      "info + episode stats down (packed rows over PCIe + host-side expansion, balanced with direct DMA)")
+        e2e_variants = {
+            "plain_pcie_copy": run_e2e(0, 0.0, True, warm=1),
+            "obs_stay_on_device": run_e2e(0, 0.0, False, warm=1),
+        }
+        e2e_variants["obs_stay_on_device"]["note"] = "actions up; reward/done/info/extra/episode stats down; observations consumed on the GPU"
+        esim.set_host_path(None, -1.0)
 
     # ------------------------------------------------------------------ optional sweep (stderr)
     if args.sweep and rank == 0:
@@ -348,7 +372,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(args, world),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_variants": e2e_variants, "gpu_launches": launches,
             "clocks": clk.summary(),
         }
         print(json.dumps(line), flush=True)

@@ -162,6 +162,17 @@ int inv_step_host(inv_sim *sim, const int8_t *a_p1, const int8_t *a_p2, void *ob
                   int32_t *episode_steps, double *episode_return);
 int inv_reset_host(inv_sim *sim, void *obs_p1, float *extra_p1, void *obs_p2, float *extra_p2);
 
+/* How inv_step_host delivers float32 observations to host memory. nthreads = 0: one plain
+ * device-to-host copy (PCIe-bound, about 7.2 KB per env). nthreads > 0 (default: the host's
+ * hardware threads, at most 32): the kernel also emits each observation as its packed 1800-bit
+ * row (256 B/env); the copy engine moves the float32 data of a fraction `dma_fraction` of the envs
+ * while `nthreads` host threads expand the packed rows of the rest with non-temporal stores.
+ * dma_fraction < 0 = keep balancing the two legs from their measured rates (default). Format
+ * conversion only; other dtypes and batches under 4096 envs always use the plain copy. */
+int inv_set_host_path(inv_sim *sim, int nthreads, double dma_fraction);
+int inv_get_host_path(const inv_sim *sim, int *nthreads, double *dma_fraction, double *last_dma_s,
+                      double *last_expand_s);
+
 /* page-locked host memory for the *_host calls (pageable memory works too, slower) */
 int inv_host_alloc(void **out, int64_t nbytes);
 int inv_host_free(void *p);

@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libinversus_b200.so")
 SOURCES = [os.path.join(CSRC, "inversus_b200.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "inversus_kernels.cuh"),
+HOST_SOURCES = [os.path.join(CSRC, "host_expand.cpp")]  # plain C++ (AVX2 intrinsics), compiled by g++
+DEPS = SOURCES + HOST_SOURCES + [os.path.join(CSRC, "inversus_kernels.cuh"),
                   os.path.join(os.path.dirname(HERE), "include", "inversus_b200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -33,7 +34,15 @@ def is_stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into libinversus_b200.so next to this file. Cross-compiles without a GPU."""
     if force or is_stale():
-        cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
+        objs = []
+        for src in HOST_SOURCES:
+            obj = os.path.join(HERE, os.path.basename(src) + ".o")
+            cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", src, "-o", obj]
+            if verbose:
+                print(" ".join(cmd))
+            subprocess.check_call(cmd)
+            objs.append(obj)
+        cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES + objs
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -6,13 +6,20 @@
 // fails with INV_ERR_NO_DEVICE / INV_ERR_CUDA when no sm_100 device is usable.
 #include "inversus_kernels.cuh"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 using namespace inv;
+
+namespace inv_host { // host_expand.cpp
+void expand_f32(const uint32_t *bits, float *dst, int64_t lo, int64_t hi, int nthreads);
+int hardware_threads();
+} // namespace inv_host
 
 struct inv_sim {
     inv_config cfg;
@@ -32,6 +39,13 @@ struct inv_sim {
     int8_t *h_a1, *h_a2, *d_a1, *d_a2;
     uint32_t *h_status;
     cudaStream_t host_stream;
+    // host-expand path of inv_step_host (f32 obs only): packed rows device + pinned host staging
+    int host_threads;   // 0 = plain DMA of the f32 observation
+    double dma_frac;    // share of the envs whose f32 observation is copied directly (rest expanded)
+    bool dma_frac_auto;
+    uint4 *d_bits[2];
+    uint32_t *h_bits[2];
+    double last_dma_s, last_expand_s;
 };
 
 static thread_local char g_err[512] = "";
@@ -81,6 +95,7 @@ Params base_params(const inv_sim *s)
     p.count = s->n;
     p.table = s->table;
     p.obs1 = s->obs1; p.obs2 = s->obs2;
+    p.bits1 = nullptr; p.bits2 = nullptr;
     p.extra1 = s->extra1; p.extra2 = s->extra2;
     p.reward = s->reward; p.done = s->done; p.info = s->info; p.dbg = s->dbg;
     p.ep_steps = s->ep_steps; p.ep_return = s->ep_return;
@@ -248,6 +263,9 @@ int inv_create(const inv_config *cfg, inv_sim **out)
     if (cfg->mode == INV_MODE_SELFPLAY) s->cfg.flags |= INV_FLAG_P2_VIEW; // env_wrappers.py:311
     s->n = cfg->n_envs;
     s->sm_count = prop.multiProcessorCount;
+    s->host_threads = inv_host::hardware_threads() > 32 ? 32 : inv_host::hardware_threads();
+    s->dma_frac = 0.35;
+    s->dma_frac_auto = true;
     const int64_t n = s->n;
     const bool p2v = (s->cfg.flags & INV_FLAG_P2_VIEW) != 0;
     const size_t obs_bytes = (size_t)n * INV_OBS_ELEMS * obs_elem_bytes(cfg->obs_dtype);
@@ -317,6 +335,10 @@ int inv_destroy(inv_sim *s)
     if (s->h_a1) cudaFreeHost(s->h_a1);
     if (s->h_a2) cudaFreeHost(s->h_a2);
     if (s->h_status) cudaFreeHost(s->h_status);
+    for (int v = 0; v < 2; ++v) {
+        if (s->d_bits[v]) cudaFree(s->d_bits[v]);
+        if (s->h_bits[v]) cudaFreeHost(s->h_bits[v]);
+    }
     if (s->host_stream) cudaStreamDestroy(s->host_stream);
     delete s;
     return INV_OK;
@@ -356,7 +378,7 @@ int inv_reset_envs(inv_sim *s, const int64_t *idx_dev, int64_t count, void *stre
     return INV_OK;
 }
 
-int inv_step(inv_sim *s, const int8_t *a1, const int8_t *a2, void *stream)
+static int step_impl(inv_sim *s, const int8_t *a1, const int8_t *a2, void *stream, uint4 *bits1, uint4 *bits2)
 {
     if (!s || !a1) return fail(INV_ERR_INVALID_ARG, "inv_step: null argument");
     if (!s->was_reset) return fail(INV_ERR_NOT_RESET, "inv_step before inv_reset");
@@ -366,23 +388,24 @@ int inv_step(inv_sim *s, const int8_t *a1, const int8_t *a2, void *stream)
     Params p = base_params(s);
     p.a1 = a1;
     p.a2 = a2;
+    p.bits1 = bits1;
+    p.bits2 = bits2;
     CUDA_TRY((launch<OP_STEP, false>(p, s->cfg.obs_dtype, (s->cfg.flags & INV_FLAG_P2_VIEW) != 0, s->sm_count,
                                      (cudaStream_t)stream)));
     s->launches += 1;
     return INV_OK;
 }
 
-static int copy_outputs(inv_sim *s, cudaStream_t st, void *obs_p1, float *extra_p1, void *obs_p2, float *extra_p2,
-                        float *reward, uint8_t *done, uint8_t *info, int32_t *episode_steps, double *episode_return)
+int inv_step(inv_sim *s, const int8_t *a1, const int8_t *a2, void *stream)
+{
+    return step_impl(s, a1, a2, stream, nullptr, nullptr);
+}
+
+static int copy_small_outputs(inv_sim *s, cudaStream_t st, float *extra_p1, float *extra_p2, float *reward,
+                              uint8_t *done, uint8_t *info, int32_t *episode_steps, double *episode_return)
 {
     const int64_t n = s->n;
-    const size_t ob = (size_t)n * INV_OBS_ELEMS * obs_elem_bytes(s->cfg.obs_dtype);
-    if (obs_p1) CUDA_TRY(cudaMemcpyAsync(obs_p1, s->obs1, ob, cudaMemcpyDeviceToHost, st));
     if (extra_p1) CUDA_TRY(cudaMemcpyAsync(extra_p1, s->extra1, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-    if (obs_p2) {
-        if (!s->obs2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
-        CUDA_TRY(cudaMemcpyAsync(obs_p2, s->obs2, ob, cudaMemcpyDeviceToHost, st));
-    }
     if (extra_p2) {
         if (!s->extra2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
         CUDA_TRY(cudaMemcpyAsync(extra_p2, s->extra2, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
@@ -392,7 +415,72 @@ static int copy_outputs(inv_sim *s, cudaStream_t st, void *obs_p1, float *extra_
     if (info) CUDA_TRY(cudaMemcpyAsync(info, s->info, (size_t)n, cudaMemcpyDeviceToHost, st));
     if (episode_steps) CUDA_TRY(cudaMemcpyAsync(episode_steps, s->ep_steps, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (episode_return) CUDA_TRY(cudaMemcpyAsync(episode_return, s->ep_return, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    return INV_OK;
+}
+
+// Whole-observation copy straight from the device buffers (any dtype).
+static int copy_obs_plain(inv_sim *s, cudaStream_t st, void *obs_p1, void *obs_p2)
+{
+    const size_t ob = (size_t)s->n * INV_OBS_ELEMS * obs_elem_bytes(s->cfg.obs_dtype);
+    if (obs_p1) CUDA_TRY(cudaMemcpyAsync(obs_p1, s->obs1, ob, cudaMemcpyDeviceToHost, st));
+    if (obs_p2) {
+        if (!s->obs2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
+        CUDA_TRY(cudaMemcpyAsync(obs_p2, s->obs2, ob, cudaMemcpyDeviceToHost, st));
+    }
+    return INV_OK;
+}
+
+static bool use_host_expand(const inv_sim *s, const void *obs_p1, const void *obs_p2)
+{
+    return s->host_threads > 0 && s->cfg.obs_dtype == INV_OBS_F32 && (obs_p1 || obs_p2) && s->n >= 4096;
+}
+
+static int ensure_bits_staging(inv_sim *s, bool p2)
+{
+    for (int v = 0; v < (p2 ? 2 : 1); ++v) {
+        if (!s->d_bits[v]) CUDA_TRY(cudaMalloc((void **)&s->d_bits[v], (size_t)s->n * 256));
+        if (!s->h_bits[v]) CUDA_TRY(cudaMallocHost((void **)&s->h_bits[v], (size_t)s->n * 256));
+    }
+    return INV_OK;
+}
+
+// f32 observations to host memory, faster than PCIe alone: the packed rows (256 B/env) cross PCIe
+// first; then the copy engine moves the f32 data of envs [0, nA) while the host threads expand the
+// packed rows of envs [nA, n) with non-temporal stores. nA follows the measured rates of the two.
+static int copy_obs_expand(inv_sim *s, cudaStream_t st, void *obs_p1, void *obs_p2)
+{
+    const int64_t n = s->n;
+    void *dst[2] = {obs_p1, obs_p2};
+    const void *src[2] = {s->obs1, s->obs2};
+    for (int v = 0; v < 2; ++v)
+        if (dst[v]) CUDA_TRY(cudaMemcpyAsync(s->h_bits[v], s->d_bits[v], (size_t)n * 256, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st)); // small outputs + packed rows have landed
+    const int64_t nA = (int64_t)((double)n * s->dma_frac) & ~(int64_t)255;
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
+    double expand_s = 0.0;
+    std::thread ex([&] {
+        for (int v = 0; v < 2; ++v)
+            if (dst[v]) inv_host::expand_f32(s->h_bits[v], static_cast<float *>(dst[v]), nA, n, s->host_threads);
+        expand_s = std::chrono::duration<double>(clk::now() - t0).count();
+    });
+    cudaError_t ce = cudaSuccess;
+    if (nA > 0)
+        for (int v = 0; v < 2 && ce == cudaSuccess; ++v)
+            if (dst[v]) ce = cudaMemcpyAsync(dst[v], src[v], (size_t)nA * INV_OBS_ELEMS * 4, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    const double dma_s = std::chrono::duration<double>(clk::now() - t0).count();
+    ex.join();
+    if (ce != cudaSuccess) return fail(INV_ERR_CUDA, "observation copy: %s", cudaGetErrorString(ce));
+    s->last_dma_s = dma_s;
+    s->last_expand_s = expand_s;
+    if (s->dma_frac_auto && expand_s > 0.0) { // balance the two legs from their measured rates
+        const double r_exp = (double)(n - nA) / expand_s;
+        const double r_dma = nA > 0 && dma_s > 0.0 ? (double)nA / dma_s : r_exp * 0.5;
+        double f = r_dma / (r_dma + r_exp);
+        f = f < 0.0 ? 0.0 : (f > 0.9 ? 0.9 : f);
+        s->dma_frac = 0.5 * s->dma_frac + 0.5 * f;
+    }
     return INV_OK;
 }
 
@@ -404,6 +492,7 @@ int inv_step_host(inv_sim *s, const int8_t *a1, const int8_t *a2, void *obs_p1, 
     if (!s->was_reset) return fail(INV_ERR_NOT_RESET, "inv_step_host before inv_reset");
     const bool selfplay = s->cfg.mode == INV_MODE_SELFPLAY;
     if (selfplay && !a2) return fail(INV_ERR_INVALID_ARG, "opponent_policy required for selfplay mode");
+    if (obs_p2 && !s->obs2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
     const int64_t n = s->n;
     // discrete_to_action raises before anything is stepped (env_wrappers.py:302, :66)
     for (int64_t i = 0; i < n; ++i) {
@@ -419,18 +508,60 @@ int inv_step_host(inv_sim *s, const int8_t *a1, const int8_t *a2, void *obs_p1, 
         memcpy(s->h_a2, a2, (size_t)n);
         CUDA_TRY(cudaMemcpyAsync(s->d_a2, s->h_a2, (size_t)n, cudaMemcpyHostToDevice, st));
     }
-    int rc = inv_step(s, s->d_a1, selfplay ? s->d_a2 : nullptr, st);
+    const bool expand = use_host_expand(s, obs_p1, obs_p2);
+    if (expand) {
+        int rc = ensure_bits_staging(s, obs_p2 != nullptr);
+        if (rc != INV_OK) return rc;
+    }
+    int rc = step_impl(s, s->d_a1, selfplay ? s->d_a2 : nullptr, st, expand ? s->d_bits[0] : nullptr,
+                       expand && obs_p2 ? s->d_bits[1] : nullptr);
     if (rc != INV_OK) return rc;
-    return copy_outputs(s, st, obs_p1, extra_p1, obs_p2, extra_p2, reward, done, info, episode_steps, episode_return);
+    rc = copy_small_outputs(s, st, extra_p1, extra_p2, reward, done, info, episode_steps, episode_return);
+    if (rc != INV_OK) return rc;
+    if (expand) {
+        // d_bits[0] is always written by the kernel in this mode; only requested views are shipped
+        void *o1 = obs_p1, *o2 = obs_p2;
+        return copy_obs_expand(s, st, o1, o2);
+    }
+    rc = copy_obs_plain(s, st, obs_p1, obs_p2);
+    if (rc != INV_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return INV_OK;
+}
+
+int inv_set_host_path(inv_sim *s, int nthreads, double dma_fraction)
+{
+    if (!s || nthreads < 0 || nthreads > 256 || dma_fraction > 1.0) return fail(INV_ERR_INVALID_ARG, "inv_set_host_path: bad argument");
+    s->host_threads = nthreads;
+    if (dma_fraction < 0.0) { s->dma_frac_auto = true; }
+    else { s->dma_frac_auto = false; s->dma_frac = dma_fraction; }
+    return INV_OK;
+}
+
+int inv_get_host_path(const inv_sim *s, int *nthreads, double *dma_fraction, double *last_dma_s, double *last_expand_s)
+{
+    if (!s) return fail(INV_ERR_INVALID_ARG, "inv_get_host_path: null handle");
+    if (nthreads) *nthreads = s->host_threads;
+    if (dma_fraction) *dma_fraction = s->dma_frac;
+    if (last_dma_s) *last_dma_s = s->last_dma_s;
+    if (last_expand_s) *last_expand_s = s->last_expand_s;
+    return INV_OK;
 }
 
 int inv_reset_host(inv_sim *s, void *obs_p1, float *extra_p1, void *obs_p2, float *extra_p2)
 {
     if (!s) return fail(INV_ERR_INVALID_ARG, "inv_reset_host: null handle");
+    if (obs_p2 && !s->obs2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
     DeviceGuard g(s->cfg.device);
-    int rc = inv_reset(s, s->host_stream);
+    cudaStream_t st = s->host_stream;
+    int rc = inv_reset(s, st);
     if (rc != INV_OK) return rc;
-    return copy_outputs(s, s->host_stream, obs_p1, extra_p1, obs_p2, extra_p2, nullptr, nullptr, nullptr, nullptr, nullptr);
+    rc = copy_small_outputs(s, st, extra_p1, extra_p2, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc != INV_OK) return rc;
+    rc = copy_obs_plain(s, st, obs_p1, obs_p2);
+    if (rc != INV_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return INV_OK;
 }
 
 int inv_host_alloc(void **out, int64_t nbytes)

@@ -54,6 +54,7 @@ struct Params {
     const int8_t *a1, *a2;
     const uint32_t *table;   // draw table or nullptr (Philox)
     void *obs1, *obs2;
+    uint4 *bits1, *bits2;    // optional: packed observation rows, 16 x 16 B per env (host-expand path)
     float *extra1, *extra2;
     float *reward;
     uint8_t *done, *info, *dbg;
@@ -699,6 +700,27 @@ __global__ void __launch_bounds__(kThreads) inv_kernel(const Params p)
                     const int bit = c * Fmt::kBits;
                     const uint32_t w = rows[e * kRowWords + (bit >> 5)] >> (bit & 31);
                     st_stream(out + s_env[e] * Fmt::kChunks + c, Fmt::expand(w));
+                }
+            }
+        }
+        // optional packed copy of the same rows (1800 bits in 57 words, padded to 64 words = 256 B
+        // per env): what inv_step_host ships over PCIe when the host expands the observation
+        if (p.bits1) {
+#pragma unroll 1
+            for (int v = 0; v < (P2V ? 2 : 1); ++v) {
+                const uint32_t *rows = v ? rows2 : rows1;
+                uint4 *out = v ? p.bits2 : p.bits1;
+                if (!out) continue;
+                for (int g = tid; g < nvalid * 16; g += kThreads) {
+                    const int e = g >> 4, c = g & 15;
+                    const uint32_t *r = rows + e * kRowWords + 4 * c;
+                    uint4 w;
+                    w.x = (4 * c + 0 < kRowWords) ? r[0] : 0u;
+                    w.y = (4 * c + 1 < kRowWords) ? r[1] : 0u;
+                    w.z = (4 * c + 2 < kRowWords) ? r[2] : 0u;
+                    w.w = (4 * c + 3 < kRowWords) ? r[3] : 0u;
+                    const int64_t eo = INDEXED ? s_env[e] : base + e;
+                    out[eo * 16 + c] = w;
                 }
             }
         }

@@ -199,6 +199,19 @@ class BatchedInversus:
             return None if v is None else v.ctypes.data_as(C.c_void_p)
         _capi.check(self._lib.inv_reset_host(self._h.ptr, p("obs"), p("extra"), p("obs_p2"), p("extra_p2")))
 
+    def set_host_path(self, nthreads: Optional[int] = None, dma_fraction: float = -1.0) -> None:
+        """How step_host delivers f32 observations (inv_set_host_path): nthreads=0 -> one plain
+        PCIe copy; nthreads>0 -> packed rows over PCIe + host-side expansion on that many threads,
+        with `dma_fraction` of the envs still copied directly (<0 = auto-balance)."""
+        if nthreads is None:
+            nthreads = min(os.cpu_count() or 1, 32)
+        _capi.check(self._lib.inv_set_host_path(self._h.ptr, int(nthreads), float(dma_fraction)))
+
+    def host_path(self) -> dict:
+        nt, fr, td, te = C.c_int(), C.c_double(), C.c_double(), C.c_double()
+        _capi.check(self._lib.inv_get_host_path(self._h.ptr, C.byref(nt), C.byref(fr), C.byref(td), C.byref(te)))
+        return {"threads": nt.value, "dma_fraction": fr.value, "last_dma_s": td.value, "last_expand_s": te.value}
+
     def host_buffers(self, pinned: bool = True) -> dict:
         """Allocate one set of numpy output buffers for step_host (page-locked by default)."""
         n = self.num_envs

@@ -157,3 +157,32 @@ def test_step_before_reset_fails_loudly():
     s = BatchedInversus(8, seed=0)
     with pytest.raises(InversusError):
         s.step(torch.zeros(8, dtype=torch.int8, device="cuda"))
+
+
+@pytest.mark.parametrize("mode", ["dummy", "selfplay"])
+def test_host_buffer_paths_deliver_identical_observations(mode):
+    """inv_step_host: plain PCIe copy vs packed-rows + host expansion (any DMA share) must hand
+    the caller bit-identical float32 observations and outputs; checked against the device views."""
+    import torch
+    from inversus_b200 import BatchedInversus
+    n, T = 6000, 12
+    rs = np.random.RandomState(21)
+    sims = {}
+    for name, (nt, frac) in {"plain": (0, 0.0), "expand_all": (4, 0.0), "hybrid": (3, 0.5), "auto": (None, -1.0)}.items():
+        s = BatchedInversus(n, mode, "hard", 30, seed=17, auto_reset=True)
+        s.set_host_path(nt, frac)
+        s.reset()
+        sims[name] = (s, s.host_buffers(pinned=(name != "expand_all")))
+    for _ in range(T):
+        a1 = rs.randint(0, 13, n).astype(np.int8)
+        a2 = rs.randint(0, 13, n).astype(np.int8) if mode == "selfplay" else None
+        for name, (s, out) in sims.items():
+            s.step_host(a1, a2, out)
+        ref_s, ref = sims["plain"]
+        assert np.array_equal(ref["obs"], ref_s.obs.cpu().numpy())
+        for name, (s, out) in sims.items():
+            for k in ("obs", "extra", "reward", "done", "info", "episode_steps", "episode_return") + (
+                    ("obs_p2", "extra_p2") if mode == "selfplay" else ()):
+                assert np.array_equal(out[k], ref[k]), (name, k)
+    assert sims["hybrid"][0].host_path()["dma_fraction"] == 0.5
+    assert 0.0 <= sims["auto"][0].host_path()["dma_fraction"] <= 0.9
