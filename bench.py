@@ -180,7 +180,7 @@ def reference_arm(args):
                 "(oracle/inversus_oracle.c) on all host cores. Python reference measured in the builder "
                 "container: ~5e3 env-steps/s per core (SURVEY.md section 6).",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -210,6 +210,28 @@ def time_steps(sim, torch, acts, acts2, steps, first_t=0):
     return [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)], ev[0].elapsed_time(ev[steps])
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep stdout clean for the ONE JSON line: libraries (NCCL prints its version banner to fd 1)
+    are redirected to stderr for the duration of the run."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -226,6 +248,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    claim_stdout()
     rank, local_rank, world = dist_env()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -375,7 +398,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_variants": e2e_variants, "gpu_launches": launches,
             "clocks": clk.summary(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -202,6 +202,15 @@ int inv_debug_phase(inv_sim *sim, int phase, int pid, int arg, int arg2, void *s
 /* synchronises `stream`, returns and clears the sticky INV_STATUS_* bits */
 int inv_poll_status(inv_sim *sim, void *stream, uint32_t *bits);
 
+/* PPOAgent.compute_advantages (inversus_rl/ppo_agent.py:127-157) over a device-resident rollout
+ * laid out [T][N] (time-major, N envs): GAE per env, walking time backwards, float32 in the
+ * reference's operation order. last_value_dev: [N] bootstrap values or NULL for 0 (the reference
+ * always passes 0, ppo_agent.py:170). N = 1 with T = buffer length reproduces the reference's
+ * flat-list behaviour bit for bit. Runs on the current device. */
+int inv_gae(const float *reward_dev, const float *value_dev, const uint8_t *done_dev,
+            const float *last_value_dev, double gamma, double lam, int32_t T, int64_t N, float *adv_dev,
+            float *ret_dev, void *stream);
+
 /* kernel launches issued through this handle so far (bench.py's gpu_launches) */
 int64_t inv_launch_count(const inv_sim *sim);
 

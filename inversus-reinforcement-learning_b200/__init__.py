@@ -7,6 +7,7 @@ repo-root module `inversus_b200.py` registers it under the importable name `inve
 Public surface
     MultiEnvRunner, SingleInversusRLEnv, discrete_to_action   reference-shaped numpy API
     BatchedInversus                                           tensor-native API (device views)
+    InversusCNNPolicy, PPOAgent, DeviceRollout, train_*       GPU-resident PPO around it (next rows)
     shard_range, reduce_rollout_stats                         multi-GPU layout helpers
     build_library, library_path                               in-tree nvcc build of the C-ABI .so
 """
@@ -16,7 +17,8 @@ from ._capi import InversusError, library_path
 
 __all__ = ["constants", "build_library", "library_path", "InversusError", "BatchedInversus",
            "MultiEnvRunner", "SingleInversusRLEnv", "discrete_to_action", "InfoList",
-           "shard_range", "reduce_rollout_stats"]
+           "shard_range", "reduce_rollout_stats", "InversusCNNPolicy", "make_policy_from_env", "PPOAgent",
+           "DeviceRollout", "compute_gae", "train_vs_dummy", "train_selfplay"]
 
 _LAZY = {
     "BatchedInversus": ("simulator", "BatchedInversus"),
@@ -24,6 +26,13 @@ _LAZY = {
     "SingleInversusRLEnv": ("env_wrappers", "SingleInversusRLEnv"),
     "discrete_to_action": ("env_wrappers", "discrete_to_action"),
     "InfoList": ("env_wrappers", "InfoList"),
+    "InversusCNNPolicy": ("policies", "InversusCNNPolicy"),
+    "make_policy_from_env": ("policies", "make_policy_from_env"),
+    "PPOAgent": ("ppo_agent", "PPOAgent"),
+    "DeviceRollout": ("ppo_agent", "DeviceRollout"),
+    "compute_gae": ("ppo_agent", "compute_gae"),
+    "train_vs_dummy": ("training", "train_vs_dummy"),
+    "train_selfplay": ("training", "train_selfplay"),
     "shard_range": ("sharding", "shard_range"),
     "reduce_rollout_stats": ("sharding", "reduce_rollout_stats"),
 }

@@ -70,6 +70,8 @@ SYMBOLS = {
     "inv_debug_phase": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "inv_poll_status": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_uint32)]),
     "inv_launch_count": (C.c_int64, [C.c_void_p]),
+    "inv_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32,
+                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -70,6 +70,35 @@ __global__ void init_episode_kernel(uint4 *plane2, int64_t n)
     if (i < n) plane2[i] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u); // episode = "none yet", return = 0.0
 }
 
+// Generalised advantage estimation over a [T][N] rollout, one thread per env, walking time
+// backwards (ppo_agent.py:127-157). float32 arithmetic in the reference's operation order
+// (numpy 2 keeps python-float constants "weak", so every product/sum there is float32); _rn
+// intrinsics forbid fma contraction so the result is bit-identical to the numpy loop.
+// N = 1, T = len(buffer) reproduces the reference's flat-list quirk (values[t+1] of the NEXT
+// list element, whatever env it belongs to).
+__global__ void gae_kernel(const float *__restrict__ reward, const float *__restrict__ value,
+                           const uint8_t *__restrict__ done, const float *__restrict__ last_value, float gamma,
+                           float gamma_lam, int T, int64_t N, float *__restrict__ adv, float *__restrict__ ret)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float next_v = last_value ? last_value[i] : 0.0f;
+    float last = 0.0f;
+    for (int t = T - 1; t >= 0; --t) {
+        const int64_t k = (int64_t)t * N + i;
+        const float r = reward[k], v = value[k];
+        if (done[k]) {
+            last = __fsub_rn(r, v);                                            // :146-147
+        } else {
+            const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, next_v)), v); // :149
+            last = __fadd_rn(delta, __fmul_rn(gamma_lam, last));               // :150
+        }
+        adv[k] = last;                                                         // :151
+        ret[k] = __fadd_rn(last, v);                                           // :154
+        next_v = v;
+    }
+}
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev)
@@ -705,5 +734,18 @@ int inv_poll_status(inv_sim *s, void *stream, uint32_t *bits)
 }
 
 int64_t inv_launch_count(const inv_sim *s) { return s ? s->launches : 0; }
+
+int inv_gae(const float *reward_dev, const float *value_dev, const uint8_t *done_dev, const float *last_value_dev,
+            double gamma, double lam, int32_t T, int64_t N, float *adv_dev, float *ret_dev, void *stream)
+{
+    if (!reward_dev || !value_dev || !done_dev || !adv_dev || !ret_dev || T < 0 || N < 0)
+        return fail(INV_ERR_INVALID_ARG, "inv_gae: bad argument");
+    if (T == 0 || N == 0) return INV_OK;
+    const int threads = 128;
+    gae_kernel<<<(unsigned)((N + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+        reward_dev, value_dev, done_dev, last_value_dev, (float)gamma, (float)(gamma * lam), T, N, adv_dev, ret_dev);
+    CUDA_TRY(cudaGetLastError());
+    return INV_OK;
+}
 
 } // extern "C"

@@ -1,0 +1,298 @@
+"""PPO agent with a device-resident rollout: the "next" row of the hot path.
+
+Same constructor, hyper-parameters, loss and update schedule as the reference's `PPOAgent`
+(inversus_rl/ppo_agent.py:13-247): clipped surrogate + value_coef * MSE - entropy_coef * entropy,
+`epochs` passes over shuffled minibatches of `batch_size`, grad-norm clip 0.5, Adam. What changes
+is where the data lives:
+
+* `act` takes the simulator's device observations and returns device tensors (numpy in -> numpy
+  out is kept for the reference's calling convention, ppo_agent.py:68-106);
+* the rollout is stored time-major `[T, N]` on the device (`DeviceRollout`), observations as
+  80-byte packed-state snapshots that are decoded per minibatch by the simulator's K3 kernel;
+* GAE runs as one CUDA kernel (`inv_gae`), per env. The reference runs GAE over the flat
+  `[t0e0, t0e1, ..., t1e0, ...]` list so that for num_envs > 1 `values[t+1]` belongs to a
+  different env (ppo_agent.py:145-152 vs training.py:128-137); `gae_mode="reference"` reproduces
+  that bit for bit, the default `"per_env"` is the textbook estimator;
+* under `torch.distributed` the gradients are averaged with one flat NCCL all-reduce per
+  minibatch (10.25 M parameters = 41 MB fp32).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _capi
+
+
+def gae_numpy(rewards: np.ndarray, values: np.ndarray, dones: np.ndarray, last_value, gamma: float, lam: float):
+    """The reference's loop (ppo_agent.py:139-154) over [T, N] float32 arrays, per column.
+    Used for CPU tensors only (the reference's default device); CUDA tensors go through inv_gae."""
+    T, N = rewards.shape
+    adv = np.zeros_like(rewards, dtype=np.float32)
+    g, gl = np.float32(gamma), np.float32(gamma * lam)
+    nxt = np.zeros(N, np.float32) if last_value is None else np.asarray(last_value, np.float32).reshape(N).copy()
+    last = np.zeros(N, np.float32)
+    for t in range(T - 1, -1, -1):
+        r, v, d = rewards[t].astype(np.float32), values[t].astype(np.float32), dones[t].astype(bool)
+        delta_run = (r + g * nxt) - v
+        last = np.where(d, r - v, delta_run + gl * last).astype(np.float32)
+        adv[t] = last
+        nxt = v
+    return adv, adv + values.astype(np.float32)
+
+
+def compute_gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, last_value: Optional[torch.Tensor],
+                gamma: float, lam: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """GAE over a time-major [T, N] rollout. CUDA tensors: one `inv_gae` kernel launch."""
+    T, N = rewards.shape
+    if not rewards.is_cuda:
+        a, r = gae_numpy(rewards.numpy(), values.numpy(), dones.numpy(),
+                         None if last_value is None else last_value.numpy(), gamma, lam)
+        return torch.from_numpy(a), torch.from_numpy(r)
+    rewards = rewards.contiguous().float()
+    values = values.contiguous().float()
+    dones = dones.contiguous().to(torch.uint8)
+    lv = None if last_value is None else last_value.contiguous().float()
+    adv = torch.empty_like(rewards)
+    ret = torch.empty_like(rewards)
+    with torch.cuda.device(rewards.device):
+        _capi.check(_capi.load().inv_gae(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(),
+                                         None if lv is None else lv.data_ptr(), gamma, lam, T, N,
+                                         adv.data_ptr(), ret.data_ptr(),
+                                         int(torch.cuda.current_stream(rewards.device).cuda_stream)))
+    return adv, ret
+
+
+class DeviceRollout:
+    """Time-major rollout storage on the device. Observations are kept either as packed-state
+    snapshots (80 B per env-step; decoded per minibatch through `sim.obs_from_packed`) or as the
+    observation tensors themselves (`store="obs"`, small runs and parity tests)."""
+
+    def __init__(self, T: int, N: int, device, store: str = "packed", obs_dtype=torch.float32):
+        self.T, self.N, self.device, self.store = T, N, torch.device(device), store
+        self.t = 0
+        if store == "packed":
+            self.packed = torch.empty((5, T, N, 4), dtype=torch.int32, device=device)
+        else:
+            self.obs = torch.empty((T, N, 12, 10, 15), dtype=obs_dtype, device=device)
+            self.extra = torch.empty((T, N, 4), dtype=torch.float32, device=device)
+        self.actions = torch.empty((T, N), dtype=torch.int64, device=device)
+        self.log_probs = torch.empty((T, N), dtype=torch.float32, device=device)
+        self.values = torch.empty((T, N), dtype=torch.float32, device=device)
+        self.rewards = torch.empty((T, N), dtype=torch.float32, device=device)
+        self.dones = torch.empty((T, N), dtype=torch.uint8, device=device)
+
+    def reset(self):
+        self.t = 0
+
+    @property
+    def full(self) -> bool:
+        return self.t >= self.T
+
+    def store_pre(self, sim_or_obs, actions, log_probs, values):
+        """Before the env step: what the policy saw (state snapshot or obs) and what it did."""
+        t = self.t
+        if self.store == "packed":
+            self.packed[:, t].copy_(sim_or_obs.packed_state)
+        else:
+            obs, extra = sim_or_obs
+            self.obs[t].copy_(obs)
+            self.extra[t].copy_(extra)
+        self.actions[t].copy_(actions)
+        self.log_probs[t].copy_(log_probs)
+        self.values[t].copy_(values)
+
+    def store_post(self, rewards, dones):
+        """After the env step: its reward and done flag; advances the time index."""
+        self.rewards[self.t].copy_(rewards)
+        self.dones[self.t].copy_(dones)
+        self.t += 1
+
+    def minibatch_obs(self, idx: torch.Tensor, sim, obs_dtype: Optional[str] = None):
+        """Observations of flat sample indices `idx` (m = t*N + n)."""
+        if self.store == "packed":
+            T = self.t
+            flat = self.packed[:, :T].reshape(5, T * self.N, 4)
+            sel = flat.index_select(1, idx).contiguous()
+            return sim.obs_from_packed(sel, view=0, obs_dtype=obs_dtype)
+        T = self.t
+        return (self.obs[:T].reshape(T * self.N, 12, 10, 15).index_select(0, idx),
+                self.extra[:T].reshape(T * self.N, 4).index_select(0, idx))
+
+
+class PPOAgent:
+    """ppo_agent.py:13 with device-resident data. Constructor arguments as in the reference;
+    keyword-only extras: `gae_mode` ("per_env" | "reference"), `precision` ("fp32" | "bf16":
+    bf16 autocast for inference and the training forward, fp32 master weights and optimiser),
+    `shuffle` ("torch" | "numpy": the reference shuffles with np.random, ppo_agent.py:195)."""
+
+    def __init__(self, policy: nn.Module, lr: float = 1e-4, gamma: float = 0.99, lam: float = 0.95,
+                 clip_ratio: float = 0.2, epochs: int = 4, batch_size: int = 512, entropy_coef: float = 0.02,
+                 value_coef: float = 0.1, device: str = "cpu", *, gae_mode: str = "per_env",
+                 precision: str = "fp32", shuffle: str = "torch", generator: Optional[torch.Generator] = None):
+        assert gae_mode in ("per_env", "reference") and precision in ("fp32", "bf16") and shuffle in ("torch", "numpy")
+        self.device = torch.device(device)
+        self.policy = policy.to(self.device)
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=lr)
+        self.gamma, self.lam, self.clip_ratio = gamma, lam, clip_ratio
+        self.epochs, self.batch_size = epochs, batch_size
+        self.entropy_coef, self.value_coef = entropy_coef, value_coef
+        self.gae_mode, self.precision, self.shuffle, self.generator = gae_mode, precision, shuffle, generator
+        self.max_grad_norm = 0.5  # ppo_agent.py:228
+        self.reset_buffers()
+
+    # ------------------------------------------------------------------ reference-shaped list buffers
+    def reset_buffers(self) -> None:
+        self.obs_grid_buffer: List = []
+        self.obs_extra_buffer: List = []
+        self.action_buffer: List[int] = []
+        self.log_prob_buffer: List[float] = []
+        self.reward_buffer: List[float] = []
+        self.value_buffer: List[float] = []
+        self.done_buffer: List[bool] = []
+
+    def store_step(self, grid_tensor, extra_vector, action, log_prob, value, reward, done) -> None:
+        """ppo_agent.py:108-125 (one sample at a time, kept for the reference's rollout loop)."""
+        self.obs_grid_buffer.append(grid_tensor)
+        self.obs_extra_buffer.append(extra_vector)
+        self.action_buffer.append(action)
+        self.log_prob_buffer.append(log_prob)
+        self.reward_buffer.append(reward)
+        self.value_buffer.append(value)
+        self.done_buffer.append(done)
+
+    def compute_advantages(self, last_value: float = 0.0) -> Tuple[np.ndarray, np.ndarray]:
+        """ppo_agent.py:127-157 on the list buffers: GAE over the flat list (N = 1, T = len)."""
+        r = torch.tensor(self.reward_buffer, dtype=torch.float32, device=self.device).view(-1, 1)
+        v = torch.tensor(self.value_buffer, dtype=torch.float32, device=self.device).view(-1, 1)
+        d = torch.tensor(self.done_buffer, dtype=torch.uint8, device=self.device).view(-1, 1)
+        lv = torch.tensor([last_value], dtype=torch.float32, device=self.device)
+        adv, ret = compute_gae(r, v, d, lv, self.gamma, self.lam)
+        return adv.view(-1).cpu().numpy(), ret.view(-1).cpu().numpy()
+
+    # ------------------------------------------------------------------ acting
+    def _forward(self, grid, extra, train: bool):
+        if self.precision == "bf16" and grid.is_cuda:
+            if not train:
+                return self.policy.infer(grid, extra)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                logits, value = self.policy(grid.to(torch.bfloat16), extra)
+            return logits.float(), value.float()
+        return self.policy(grid.float() if grid.dtype != torch.float32 else grid, extra)
+
+    def act(self, grid_tensors, extra_vectors):
+        """ppo_agent.py:68-106. numpy in -> numpy (actions, log_probs, values) like the reference;
+        tensors in -> device tensors (no host round trip, no sync)."""
+        self.policy.eval()
+        as_numpy = not isinstance(grid_tensors, torch.Tensor)
+        with torch.no_grad():
+            grid = torch.as_tensor(grid_tensors).to(self.device)
+            extra = torch.as_tensor(extra_vectors).to(self.device)
+            logits, values = self._forward(grid, extra, train=False)
+            dist = torch.distributions.Categorical(logits=logits)
+            actions = dist.sample()
+            log_probs = dist.log_prob(actions)
+            values = values.squeeze(-1)
+        if as_numpy:
+            return actions.cpu().numpy(), log_probs.cpu().numpy(), values.cpu().numpy()
+        return actions, log_probs, values
+
+    # ------------------------------------------------------------------ update
+    def _sync_grads(self) -> None:
+        if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return
+        if torch.distributed.get_world_size() == 1:
+            return
+        grads = [p.grad for p in self.policy.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
+        flat.div_(torch.distributed.get_world_size())
+        off = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
+
+    def _permutation(self, n: int, state: dict) -> torch.Tensor:
+        if self.shuffle == "numpy":
+            # the reference shuffles ONE index array in place every epoch (ppo_agent.py:192-195),
+            # so epoch k's order is a shuffle of epoch k-1's
+            if "idx" not in state:
+                state["idx"] = np.arange(n)
+            np.random.shuffle(state["idx"])
+            return torch.from_numpy(state["idx"].copy()).to(self.device)
+        return torch.randperm(n, device=self.device, generator=self.generator)
+
+    def _run_epochs(self, n: int, fetch: Callable[[torch.Tensor], Tuple[torch.Tensor, torch.Tensor]],
+                    actions, old_log_probs, advantages, returns) -> Dict[str, float]:
+        self.policy.train()
+        sums = torch.zeros(3, device=self.device)
+        num_updates = 0
+        perm_state: dict = {}
+        for _ in range(self.epochs):
+            perm = self._permutation(n, perm_state)
+            for start in range(0, n, self.batch_size):
+                idx = perm[start:start + self.batch_size]
+                grid, extra = fetch(idx)
+                logits, values = self._forward(grid, extra, train=True)
+                dist = torch.distributions.Categorical(logits=logits)  # same ops as ppo_agent.py:211-213
+                new_log_probs = dist.log_prob(actions[idx])
+                entropy = dist.entropy().mean()
+                ratio = torch.exp(new_log_probs - old_log_probs[idx])
+                adv = advantages[idx]
+                policy_loss = -torch.min(ratio * adv, torch.clamp(ratio, 1.0 - self.clip_ratio, 1.0 + self.clip_ratio) * adv).mean()
+                value_loss = F.mse_loss(values.squeeze(-1), returns[idx])
+                loss = policy_loss + self.value_coef * value_loss - self.entropy_coef * entropy
+                self.optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+                self._sync_grads()
+                torch.nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
+                self.optimizer.step()
+                sums += torch.stack([policy_loss.detach(), value_loss.detach(), entropy.detach()])
+                num_updates += 1
+        p, v, e = (sums / max(num_updates, 1)).tolist()  # the only host sync of the update
+        return {"policy_loss": p, "value_loss": v, "entropy": e}
+
+    def update(self, rollout: Optional[DeviceRollout] = None, sim=None, last_value: Optional[torch.Tensor] = None
+               ) -> Dict[str, float]:
+        """ppo_agent.py:159-247. With no arguments it consumes the list buffers filled by
+        `store_step` (reference calling convention); with a `DeviceRollout` it trains from the
+        device-resident rollout, decoding packed observations through `sim` per minibatch."""
+        if rollout is None:
+            return self._update_from_lists()
+        T, N = rollout.t, rollout.N
+        if T == 0:
+            return {}
+        r, v, d = rollout.rewards[:T], rollout.values[:T], rollout.dones[:T]
+        if self.gae_mode == "reference":  # flat-list GAE, bootstrap 0 (ppo_agent.py:127,170)
+            adv, ret = compute_gae(r.reshape(-1, 1), v.reshape(-1, 1), d.reshape(-1, 1), None, self.gamma, self.lam)
+        else:
+            adv, ret = compute_gae(r, v, d, last_value, self.gamma, self.lam)
+        adv, ret = adv.reshape(-1), ret.reshape(-1)
+        adv = (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-8)  # ppo_agent.py:173 (numpy std, ddof 0)
+        obs_dtype = "bf16" if self.precision == "bf16" else "f32"
+        stats = self._run_epochs(T * N, lambda idx: rollout.minibatch_obs(idx, sim, obs_dtype),
+                                 rollout.actions[:T].reshape(-1), rollout.log_probs[:T].reshape(-1), adv, ret)
+        rollout.reset()
+        return stats
+
+    def _update_from_lists(self) -> Dict[str, float]:
+        if len(self.obs_grid_buffer) == 0:
+            return {}
+        adv_np, ret_np = self.compute_advantages()
+        adv_np = (adv_np - adv_np.mean()) / (adv_np.std() + 1e-8)
+        dev = self.device
+        obs_grid = torch.as_tensor(np.stack([np.asarray(o) for o in self.obs_grid_buffer]), dtype=torch.float32).to(dev)
+        obs_extra = torch.as_tensor(np.stack([np.asarray(o) for o in self.obs_extra_buffer]), dtype=torch.float32).to(dev)
+        actions = torch.as_tensor(self.action_buffer, dtype=torch.int64).to(dev)
+        old_lp = torch.as_tensor(self.log_prob_buffer, dtype=torch.float32).to(dev)
+        adv = torch.as_tensor(adv_np, dtype=torch.float32).to(dev)
+        ret = torch.as_tensor(ret_np, dtype=torch.float32).to(dev)
+        stats = self._run_epochs(len(self.action_buffer), lambda idx: (obs_grid[idx], obs_extra[idx]),
+                                 actions, old_lp, adv, ret)
+        self.reset_buffers()
+        return stats

@@ -1,0 +1,252 @@
+"""GPU-resident PPO training loop: trainer glue around the batched simulator.
+
+Mirrors the reference's entry points and flags (inversus_rl/training.py:53 train_vs_dummy, :204
+train_selfplay, :378 main; same `--mode/--num_envs/--total_steps/--log_dir/--opponent_difficulty/
+--load_model`, same 8-column training_log.csv, same policy_final.pt / checkpoint files, opponent
+snapshot every 20 000 steps), but nothing in the rollout leaves the GPU: the policy reads the
+simulator's observation buffers, samples int8 action ids, and the fused step kernel consumes them
+on the same stream. One process per GPU under torchrun: every rank owns a shard of the envs
+(no communication in the step path), gradients are averaged with one NCCL all-reduce per
+minibatch and the four rollout statistics with one more.
+
+    python -m inversus_b200.training --mode vs_dummy --num_envs 4 --total_steps 100000     # README quickstart
+    torchrun --nproc-per-node 8 -m inversus_b200.training --num_envs 8388608 --opponent_difficulty hard ...
+"""
+from __future__ import annotations
+
+import argparse
+import csv
+import os
+import time
+from collections import deque
+from typing import Optional
+
+import torch
+
+from .constants import INFO_WIN
+from .policies import InversusCNNPolicy
+from .ppo_agent import DeviceRollout, PPOAgent
+from .sharding import dist_env, reduce_rollout_stats, shard_range
+from .simulator import BatchedInversus
+
+OPPONENT_UPDATE_FREQ = 20000  # training.py:265
+
+
+class TrainingLogger:
+    """training.py:16-50: the same training_log.csv columns, so visualize_training.py keeps working;
+    throughput goes to a second file."""
+
+    COLUMNS = ["step", "episode", "avg_reward", "win_rate", "avg_ep_len", "policy_loss", "value_loss", "entropy"]
+
+    def __init__(self, log_dir: str):
+        os.makedirs(log_dir, exist_ok=True)
+        self.log_dir = log_dir
+        self.csv_path = os.path.join(log_dir, "training_log.csv")
+        self.perf_path = os.path.join(log_dir, "throughput_log.csv")
+        with open(self.csv_path, "w", newline="") as f:
+            csv.writer(f).writerow(self.COLUMNS)
+        with open(self.perf_path, "w", newline="") as f:
+            csv.writer(f).writerow(["step", "elapsed_s", "samples_per_s", "rollout_env_steps_per_s", "update_s"])
+
+    def log(self, step, episode, avg_reward, win_rate, avg_ep_len, policy_loss=0.0, value_loss=0.0, entropy=0.0):
+        with open(self.csv_path, "a", newline="") as f:
+            csv.writer(f).writerow([step, episode, avg_reward, win_rate, avg_ep_len, policy_loss, value_loss, entropy])
+
+    def log_perf(self, step, elapsed, samples_per_s, rollout_rate, update_s):
+        with open(self.perf_path, "a", newline="") as f:
+            csv.writer(f).writerow([step, elapsed, samples_per_s, rollout_rate, update_s])
+
+
+def _init_distributed():
+    rank, local_rank, world = dist_env()
+    if world > 1 and not torch.distributed.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    return rank, local_rank, world
+
+
+def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000, log_dir: Optional[str] = None,
+          opponent_difficulty: str = "easy", load_model: Optional[str] = None, *, precision: str = "bf16",
+          rollout_steps: Optional[int] = None, batch_size: Optional[int] = None, epochs: int = 4, lr: float = 1e-4,
+          reference_gae: bool = False, seed: Optional[int] = None, max_episode_steps: int = 500,
+          save: bool = True, quiet: bool = False) -> dict:
+    """Shared body of train_vs_dummy / train_selfplay. `num_envs` is the GLOBAL env count; under
+    torchrun each rank simulates its shard. Returns a summary dict (steps, episodes, win_rate,
+    samples_per_s, ...)."""
+    assert mode in ("vs_dummy", "selfplay")
+    rank, local_rank, world = _init_distributed()
+    dev = torch.device("cuda", local_rank if world > 1 else torch.cuda.current_device())
+    first, n_local = shard_range(num_envs, rank, world)
+    log_dir = log_dir or f"runs/inversus_{mode}_envs{num_envs}"
+    say = (lambda *a: None) if (quiet or rank != 0) else print
+    say(f"Training {mode} with num_envs={num_envs} ({world} GPU(s), {n_local} envs on this rank), "
+        f"total_steps={total_steps}, log_dir={log_dir}, precision={precision}")
+
+    if seed is not None:
+        torch.manual_seed(seed + rank)
+    selfplay = mode == "selfplay"
+    sim = BatchedInversus(n_local, "selfplay" if selfplay else "dummy", opponent_difficulty, max_episode_steps,
+                          seed=seed, device=dev.index, obs_dtype="bf16" if precision == "bf16" else "f32",
+                          auto_reset=True, env_id_base=first)
+    policy = InversusCNNPolicy()
+    if load_model:  # training.py:83-90
+        policy.load_state_dict(torch.load(load_model, map_location="cpu"))
+        say(f"Loaded {load_model}")
+    if world > 1:  # identical initial weights on every rank
+        policy = policy.to(dev)
+        for p in policy.parameters():
+            torch.distributed.broadcast(p.data, src=0)
+    target_policy = None
+    if selfplay:  # training.py:237-240: the opponent starts as a clone of the learner
+        target_policy = InversusCNNPolicy().to(dev)
+        target_policy.load_state_dict(policy.state_dict())
+        target_policy.eval()
+
+    # training.py:105-107: at least 2048 samples and 128 steps per env per update
+    steps_per_env = rollout_steps or max(2048 // max(num_envs, 1), 128)
+    if batch_size is None:
+        batch_size = 512 if num_envs * steps_per_env <= 1 << 16 else 16384
+    agent = PPOAgent(policy, lr=lr, epochs=epochs, batch_size=batch_size, device=str(dev), precision=precision,
+                     gae_mode="reference" if reference_gae else "per_env")
+    rollout = DeviceRollout(steps_per_env, n_local, dev, store="packed")
+    logger = TrainingLogger(log_dir) if rank == 0 else None
+
+    obs, extra = sim.reset()
+    step_count = last_log_step = last_opponent_update = episode_count = 0
+    recent = deque(maxlen=100)  # (return, length, win) of the last 100 episodes (training.py:164-166)
+    exact_recent = num_envs <= 256 and world == 1
+    acc = torch.zeros(4, dtype=torch.float64, device=dev)  # episodes, wins, return sum, length sum (since last log)
+    update_stats: dict = {}
+    window = {"steps": 0, "episodes": 0.0, "wins": 0.0}  # last logging window (all ranks)
+    window_start_step = 0
+    t_start = time.time()
+    rollout_time = update_time = 0.0
+    rollout_env_steps = 0
+
+    def opponent_actions():
+        # P2's view of the pre-step state (env_wrappers.py:311) is what the last step/reset emitted
+        with torch.no_grad():
+            logits, _ = (target_policy.infer(sim.obs_p2, sim.extra_p2) if precision == "bf16"
+                         else target_policy(sim.obs_p2, sim.extra_p2))
+            return torch.distributions.Categorical(logits=logits).sample().to(torch.int8)
+
+    while step_count < total_steps:
+        t0 = time.time()
+        for _ in range(steps_per_env):
+            actions, log_probs, values = agent.act(obs, extra)
+            rollout.store_pre(sim, actions, log_probs, values)
+            a2 = opponent_actions() if selfplay else None
+            (obs, extra), rewards, dones, info = sim.step(actions.to(torch.int8), a2)
+            rollout.store_post(rewards, dones)
+            d = dones.bool()
+            acc += torch.stack([d.sum(), ((info & INFO_WIN) != 0).sum(),
+                                torch.where(d, sim.episode_return, 0.0).sum(),
+                                torch.where(d, sim.episode_steps, 0).sum()]).to(torch.float64)
+            if exact_recent:  # small runs: the reference's exact last-100-episodes window
+                dn = d.nonzero().flatten().tolist()
+                if dn:
+                    er, es, inf = sim.episode_return.tolist(), sim.episode_steps.tolist(), info.tolist()
+                    for i in dn:
+                        recent.append((er[i], es[i], 1 if inf[i] & INFO_WIN else 0))
+            step_count += num_envs
+            rollout_env_steps += num_envs
+            if step_count >= total_steps:
+                break
+        torch.cuda.synchronize(dev)
+        t1 = time.time()
+        # bootstrap with the value of the state after the last step (per-env GAE only; the
+        # reference bootstraps with 0, ppo_agent.py:170)
+        last_value = None
+        if not reference_gae:
+            last_value = agent.act(obs, extra)[2]
+        update_stats = agent.update(rollout, sim, last_value)
+        torch.cuda.synchronize(dev)
+        t2 = time.time()
+        rollout_time += t1 - t0
+        update_time += t2 - t1
+
+        if selfplay and step_count - last_opponent_update >= OPPONENT_UPDATE_FREQ:  # training.py:331-334
+            target_policy.load_state_dict(policy.state_dict())
+            last_opponent_update = step_count
+
+        if step_count - last_log_step >= 1000 or step_count >= total_steps:  # training.py:172
+            ep, wins, rsum, lsum = reduce_rollout_stats(*acc.tolist(), device=dev)
+            acc.zero_()
+            episode_count += int(ep)
+            window = {"steps": step_count - window_start_step, "episodes": ep, "wins": wins}
+            window_start_step = step_count
+            if exact_recent and recent:
+                avg_reward = sum(r for r, _, _ in recent) / len(recent)
+                avg_len = sum(s for _, s, _ in recent) / len(recent)
+                win_rate = sum(w for _, _, w in recent) / len(recent)
+            else:
+                avg_reward, avg_len, win_rate = (rsum / ep, lsum / ep, wins / ep) if ep > 0 else (0.0, 0.0, 0.0)
+            elapsed = time.time() - t_start
+            if rank == 0 and episode_count > 0:
+                last_log_step = step_count
+                logger.log(step_count, episode_count, avg_reward, win_rate, avg_len, update_stats.get("policy_loss", 0.0),
+                           update_stats.get("value_loss", 0.0), update_stats.get("entropy", 0.0))
+                logger.log_perf(step_count, elapsed, step_count / elapsed, rollout_env_steps / max(rollout_time, 1e-9),
+                                t2 - t1)
+                say(f"Step {step_count}/{total_steps} | Episodes: {episode_count} | Avg Reward: {avg_reward:.3f} | "
+                    f"Win Rate: {win_rate:.3f} | Avg Ep Len: {avg_len:.1f} | Time: {elapsed:.1f}s | "
+                    f"{step_count / elapsed:,.0f} samples/s")
+            if save and rank == 0 and step_count % 50000 == 0 and step_count > 0:  # training.py:193
+                torch.save(policy.state_dict(), os.path.join(log_dir, f"policy_checkpoint_{step_count}.pt"))
+
+    elapsed = time.time() - t_start
+    if save and rank == 0:
+        torch.save(policy.state_dict(), os.path.join(log_dir, "policy_final.pt"))  # training.py:199-200
+    summary = {"steps": step_count, "episodes": episode_count, "elapsed_s": elapsed,
+               "samples_per_s": step_count / elapsed, "rollout_s": rollout_time, "update_s": update_time,
+               "rollout_env_steps_per_s": rollout_env_steps / max(rollout_time, 1e-9),
+               "win_rate": win_rate if episode_count else None, "avg_reward": avg_reward if episode_count else None,
+               "avg_ep_len": avg_len if episode_count else None, **update_stats,
+               "last_window": window,
+               "wins_per_kstep": 1e3 * window["wins"] / max(window["steps"], 1),
+               "n_gpus": world, "num_envs": num_envs, "steps_per_env": steps_per_env, "batch_size": batch_size,
+               "precision": precision}
+    sim.close()
+    return summary
+
+
+def train_vs_dummy(num_envs: int = 1, total_steps: int = 500_000, log_dir: str = "runs/inversus_vs_dummy",
+                   opponent_difficulty: str = "easy", load_model: Optional[str] = None, **kw) -> dict:
+    """training.py:53-201."""
+    return train("vs_dummy", num_envs, total_steps, log_dir, opponent_difficulty, load_model, **kw)
+
+
+def train_selfplay(num_envs: int = 1, total_steps: int = 500_000, log_dir: str = "runs/inversus_selfplay",
+                   load_model: Optional[str] = None, **kw) -> dict:
+    """training.py:204-375."""
+    return train("selfplay", num_envs, total_steps, log_dir, "easy", load_model, **kw)
+
+
+def main(argv=None):
+    """training.py:378-407 -- same flags; `--num_envs` is no longer capped at 16."""
+    ap = argparse.ArgumentParser(description="Train INVERSUS RL agent (GPU-resident rollout)")
+    ap.add_argument("--mode", choices=["vs_dummy", "selfplay"], default="vs_dummy")
+    ap.add_argument("--num_envs", type=int, default=1, help="Number of parallel environments (global)")
+    ap.add_argument("--total_steps", type=int, default=500000)
+    ap.add_argument("--log_dir", type=str, default=None)
+    ap.add_argument("--opponent_difficulty", type=str, default="easy", choices=["easy", "hard"])
+    ap.add_argument("--load_model", type=str, default=None)
+    ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--rollout_steps", type=int, default=None, help="env steps per update (default: reference rule)")
+    ap.add_argument("--batch_size", type=int, default=None)
+    ap.add_argument("--reference-gae", action="store_true", help="flat-list GAE exactly like ppo_agent.py:127-157")
+    ap.add_argument("--seed", type=int, default=None)
+    a = ap.parse_args(argv)
+    log_dir = a.log_dir or f"runs/inversus_{a.mode}_envs{a.num_envs}"
+    out = train(a.mode, a.num_envs, a.total_steps, log_dir, a.opponent_difficulty, a.load_model,
+                precision=a.precision, rollout_steps=a.rollout_steps, batch_size=a.batch_size,
+                reference_gae=a.reference_gae, seed=a.seed)
+    if dist_env()[0] == 0:
+        print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in out.items()})
+    if torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
