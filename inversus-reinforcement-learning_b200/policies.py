@@ -5,8 +5,8 @@ Architecture and parameter names follow inversus_rl/policies.py:11-108 so that t
 (LayerNorm over [C,H,W]), one residual around conv4, and two MLP heads `fc_actor` / `fc_critic`
 (19204 -> 256 -> 128 -> 13 | 1) on the flattened features concatenated with the 4 extra
 features. This is the only dense contraction in the system and stays in PyTorch (north star):
-`forward` is the plain module-dtype path (fp32 = the parity path); `infer` runs the same weights
-under bf16 autocast in channels-last layout with the two 19204-wide head GEMMs fused into one.
+`forward` is the plain module-dtype path (fp32 = the parity path); `forward_bf16` / `infer` run the
+same weights in bf16, channels-last end to end, with the two 19204-wide head GEMMs fused into one.
 """
 from __future__ import annotations
 
@@ -58,20 +58,77 @@ class InversusCNNPolicy(nn.Module):
         x = torch.cat([self._trunk(grid).flatten(1), extra_vector.to(p.dtype)], dim=1)
         return self.fc_actor(x), self.fc_critic(x)
 
-    # ------------------------------------------------------------------ bf16 tensor-core inference
-    def infer(self, grid_tensor: torch.Tensor, extra_vector: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Inference under bf16 autocast, channels-last, actor/critic first layers as one GEMM.
-        Accepts f32/bf16/u8 observation planes (all hold only 0/1). Returns fp32 logits and value."""
-        with torch.autocast(device_type=grid_tensor.device.type, dtype=torch.bfloat16):
-            grid = grid_tensor.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-            feat = self._trunk(grid).flatten(1)
-            x = torch.cat([feat.to(torch.bfloat16), extra_vector.to(torch.bfloat16)], dim=1)
-            a0, c0 = self.fc_actor[0], self.fc_critic[0]
-            h = F.relu(F.linear(x, torch.cat([a0.weight, c0.weight], 0), torch.cat([a0.bias, c0.bias], 0)))
-            ha, hc = h[:, : a0.out_features], h[:, a0.out_features:]
-            logits = self.fc_actor[4](F.relu(self.fc_actor[2](ha)))
-            value = self.fc_critic[4](F.relu(self.fc_critic[2](hc)))
+    # ------------------------------------------------------------------ bf16 tensor-core path
+    def _prepare_bf16(self) -> dict:
+        """bf16 working copies of the parameters in the layouts the fast path wants (differentiable
+        w.r.t. the fp32 masters): channels-last conv filters, HWC-ordered LayerNorm affines, and the
+        fused head matrix with its K dimension split into HWC-ordered trunk columns + padded extras."""
+        bf = torch.bfloat16
+        H, W, nf = self.height, self.width, self.feature_dim
+        prep = {}
+        for i in (1, 2, 3, 4):
+            conv, norm = getattr(self, f"conv{i}"), getattr(self, f"norm{i}")
+            prep[f"cw{i}"] = conv.weight.to(bf).contiguous(memory_format=torch.channels_last)
+            prep[f"cb{i}"] = conv.bias.to(bf)
+            prep[f"nw{i}"] = norm.weight.permute(1, 2, 0).to(bf).contiguous()
+            prep[f"nb{i}"] = norm.bias.permute(1, 2, 0).to(bf).contiguous()
+        a0, c0 = self.fc_actor[0], self.fc_critic[0]
+        w0 = torch.cat([a0.weight, c0.weight], 0)                # [2*hidden, 19200 + extra]
+        c = nf // (H * W)
+        prep["w_feat"] = w0[:, :nf].to(bf).reshape(-1, c, H * W).permute(0, 2, 1).reshape(-1, nf)  # CHW -> HWC columns
+        pad = (8 - self.extra_dim % 8) % 8
+        prep["w_extra"] = F.pad(w0[:, nf:], (0, pad)).to(bf)
+        prep["b0"] = torch.cat([a0.bias, c0.bias], 0).to(bf)
+        for name, seq in (("actor", self.fc_actor), ("critic", self.fc_critic)):
+            for k in (2, 4):
+                prep[f"{name}_w{k}"] = seq[k].weight.to(bf)
+                prep[f"{name}_b{k}"] = seq[k].bias.to(bf)
+        return prep
+
+    def _forward_prepared(self, prep: dict, grid_tensor: torch.Tensor, extra_vector: torch.Tensor):
+        bf = torch.bfloat16
+        H, W = self.height, self.width
+        x = grid_tensor.to(bf).contiguous(memory_format=torch.channels_last)
+        res = None
+        for i in (1, 2, 3, 4):
+            y = F.conv2d(x, prep[f"cw{i}"], prep[f"cb{i}"], padding=1)
+            if i == 4:
+                y = y + res                                      # residual around conv4 (policies.py:98-100)
+            yp = y.permute(0, 2, 3, 1)                           # [B,H,W,C] view of channels-last memory
+            yp = F.layer_norm(yp, (H, W, yp.shape[-1]), prep[f"nw{i}"], prep[f"nb{i}"], getattr(self, f"norm{i}").eps)
+            x = F.relu(yp).permute(0, 3, 1, 2)                   # back to an NCHW view, still channels-last
+            if i == 3:
+                res = x
+        feat = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)     # [B, H*W*C] without a copy
+        ex = F.pad(extra_vector.to(bf), (0, prep["w_extra"].shape[1] - self.extra_dim))
+        h = F.relu(F.linear(feat, prep["w_feat"], prep["b0"]) + F.linear(ex, prep["w_extra"]))
+        n_a = self.fc_actor[0].out_features
+        ha, hc = h[:, :n_a], h[:, n_a:]
+        logits = F.linear(F.relu(F.linear(ha, prep["actor_w2"], prep["actor_b2"])), prep["actor_w4"], prep["actor_b4"])
+        value = F.linear(F.relu(F.linear(hc, prep["critic_w2"], prep["critic_b2"])), prep["critic_w4"], prep["critic_b4"])
         return logits.float(), value.float()
+
+    def forward_bf16(self, grid_tensor: torch.Tensor, extra_vector: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Same function in bf16 with fp32 master weights (differentiable; used for the PPO update
+        when precision="bf16"). Everything stays channels-last so cuDNN never converts layouts:
+        LayerNorm([C,H,W]) runs on the contiguous [B,H,W,C] view with an HWC-permuted copy of its
+        affine parameters and bf16 I/O (fp32 statistics inside the kernel); the two 19204-wide head
+        GEMMs are fused into one whose K dimension is split into the 19200 trunk features (16-byte
+        aligned rows, weight columns permuted to HWC order so activations are never transposed)
+        and the 4 extra features. Accepts f32/bf16/u8 observation planes (they hold only 0/1).
+        Returns fp32 logits and value."""
+        return self._forward_prepared(self._prepare_bf16(), grid_tensor, extra_vector)
+
+    @torch.no_grad()
+    def infer(self, grid_tensor: torch.Tensor, extra_vector: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Rollout inference (no grad) through the bf16 path. The prepared bf16 weights are cached
+        and rebuilt only when a parameter changed (optimizer steps bump tensor versions)."""
+        key = tuple(p._version for p in self.parameters()) + (str(self.conv1.weight.device),)
+        cache = getattr(self, "_infer_cache", None)
+        if cache is None or cache[0] != key:
+            cache = (key, self._prepare_bf16())
+            object.__setattr__(self, "_infer_cache", cache)
+        return self._forward_prepared(cache[1], grid_tensor, extra_vector)
 
 
 def make_policy_from_env(env=None) -> InversusCNNPolicy:

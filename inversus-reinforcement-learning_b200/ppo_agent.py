@@ -177,11 +177,7 @@ class PPOAgent:
     # ------------------------------------------------------------------ acting
     def _forward(self, grid, extra, train: bool):
         if self.precision == "bf16" and grid.is_cuda:
-            if not train:
-                return self.policy.infer(grid, extra)
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                logits, value = self.policy(grid.to(torch.bfloat16), extra)
-            return logits.float(), value.float()
+            return self.policy.forward_bf16(grid, extra) if train else self.policy.infer(grid, extra)
         return self.policy(grid.float() if grid.dtype != torch.float32 else grid, extra)
 
     def act(self, grid_tensors, extra_vectors):

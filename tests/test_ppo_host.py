@@ -111,3 +111,45 @@ def test_training_logger_writes_the_reference_columns(tmp_path):
     rows = open(os.path.join(str(tmp_path), "training_log.csv")).read().splitlines()
     assert rows[0] == "step,episode,avg_reward,win_rate,avg_ep_len,policy_loss,value_loss,entropy"  # training.py:28-31
     assert rows[1].startswith("2048,3,1.5,0.33,20.0,")
+
+
+def test_bf16_path_matches_fp32_forward_and_gradients():
+    """forward_bf16 restructures the network (channels-last, HWC-permuted LayerNorm parameters and
+    head-weight columns, fused + K-split head GEMM). Against the plain fp32 forward with
+    randomised LayerNorm affines: outputs within 2e-2 absolute, every parameter gradient with
+    cosine similarity > 0.99 (bf16 has an 8-bit mantissa)."""
+    import torch.nn.functional as F
+    from inversus_b200.policies import InversusCNNPolicy
+    torch.manual_seed(0)
+    m = InversusCNNPolicy()
+    for i in (1, 2, 3, 4):
+        n = getattr(m, f"norm{i}")
+        n.weight.data.uniform_(0.5, 1.5)
+        n.bias.data.uniform_(-0.5, 0.5)
+    g = (torch.rand(5, 12, 10, 15) > 0.7).float()
+    e = torch.rand(5, 4)
+    a, b = m(g, e), m.forward_bf16(g, e)
+    assert (a[0] - b[0]).abs().max() < 2e-2 and (a[1] - b[1]).abs().max() < 2e-2
+    ga = torch.autograd.grad(a[0].sum() + a[1].sum(), list(m.parameters()))
+    gb = torch.autograd.grad(b[0].sum() + b[1].sum(), list(m.parameters()))
+    for (name, _), x, y in zip(m.named_parameters(), ga, gb):
+        assert F.cosine_similarity(x.flatten(), y.flatten(), dim=0) > 0.99, name
+    for obs in (g.to(torch.uint8), g.to(torch.bfloat16)):
+        c = m.infer(obs, e)
+        assert torch.equal(c[0], b[0].detach()) and torch.equal(c[1], b[1].detach())
+
+
+def test_inference_cache_follows_optimizer_steps():
+    from inversus_b200.policies import InversusCNNPolicy
+    torch.manual_seed(1)
+    m = InversusCNNPolicy()
+    g, e = (torch.rand(3, 12, 10, 15) > 0.6).float(), torch.rand(3, 4)
+    a = m.infer(g, e)
+    assert torch.equal(m.infer(g, e)[0], a[0])          # served from the cache
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+    loss = m(g, e)[0].sum()
+    loss.backward()
+    opt.step()                                            # in-place update bumps tensor versions
+    b = m.infer(g, e)
+    assert not torch.equal(a[0], b[0])
+    assert torch.equal(b[0], m.forward_bf16(g, e)[0].detach())
