@@ -352,7 +352,9 @@ def main():
         # headline: every output of MultiEnvRunner.step, fp32 observations included, lands in host
         # buffers. Packed rows cross PCIe and are expanded on the host threads while the copy engine
         # moves the rest directly (inv_set_host_path, auto-balanced).
-        e2e = run_e2e(None, -1.0, True, warm=6)
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        host_threads = max(1, min(32, (os.cpu_count() or 1) // max(local_world, 1)))  # ranks share the host cores
+        e2e = run_e2e(host_threads, -1.0, True, warm=6)
         e2e["api"] = ("inv_step_host (C ABI), pinned host buffers: int8 action ids up; fp32 obs + extra + reward + done + "
                       "info + episode stats down (packed rows over PCIe + host-side expansion, balanced with direct DMA)")
         e2e_variants = {
@@ -360,7 +362,7 @@ def main():
             "obs_stay_on_device": run_e2e(0, 0.0, False, warm=1),
         }
         e2e_variants["obs_stay_on_device"]["note"] = "actions up; reward/done/info/extra/episode stats down; observations consumed on the GPU"
-        esim.set_host_path(None, -1.0)
+        esim.set_host_path(host_threads, -1.0)
 
     # ------------------------------------------------------------------ optional sweep (stderr)
     if args.sweep and rank == 0:

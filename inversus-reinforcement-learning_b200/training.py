@@ -123,6 +123,8 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
     t_start = time.time()
     rollout_time = update_time = 0.0
     rollout_env_steps = 0
+    iters = []      # (samples, rollout seconds, update seconds) per iteration
+    iter_steps = 0
 
     def opponent_actions():
         # P2's view of the pre-step state (env_wrappers.py:311) is what the last step/reset emitted
@@ -165,6 +167,8 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
         t2 = time.time()
         rollout_time += t1 - t0
         update_time += t2 - t1
+        iters.append((rollout.T * num_envs if not iters else step_count - iter_steps, t1 - t0, t2 - t1))
+        iter_steps = step_count
 
         if selfplay and step_count - last_opponent_update >= OPPONENT_UPDATE_FREQ:  # training.py:331-334
             target_policy.load_state_dict(policy.state_dict())
@@ -203,12 +207,21 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
                "rollout_env_steps_per_s": rollout_env_steps / max(rollout_time, 1e-9),
                "win_rate": win_rate if episode_count else None, "avg_reward": avg_reward if episode_count else None,
                "avg_ep_len": avg_len if episode_count else None, **update_stats,
+               "steady_state": _steady(iters),
                "last_window": window,
                "wins_per_kstep": 1e3 * window["wins"] / max(window["steps"], 1),
                "n_gpus": world, "num_envs": num_envs, "steps_per_env": steps_per_env, "batch_size": batch_size,
                "precision": precision}
     sim.close()
     return summary
+
+
+def _steady(iters):
+    """Throughput over the iterations after the first (which pays cuDNN/NCCL/allocator warm-up)."""
+    body = iters[1:] if len(iters) > 1 else iters
+    n, r, u = (sum(x[i] for x in body) for i in range(3))
+    return {"iterations": len(body), "samples_per_s": n / max(r + u, 1e-9), "rollout_env_steps_per_s": n / max(r, 1e-9),
+            "update_samples_per_s": n / max(u, 1e-9)}
 
 
 def train_vs_dummy(num_envs: int = 1, total_steps: int = 500_000, log_dir: str = "runs/inversus_vs_dummy",

@@ -18,7 +18,7 @@ from inversus_b200.sharding import dist_env  # noqa: E402
 from inversus_b200.training import train  # noqa: E402
 
 KEYS = ("n_gpus", "num_envs", "steps", "steps_per_env", "batch_size", "precision", "elapsed_s", "samples_per_s",
-        "rollout_s", "update_s", "rollout_env_steps_per_s", "episodes", "win_rate", "policy_loss", "value_loss", "entropy")
+        "rollout_s", "update_s", "rollout_env_steps_per_s", "steady_state", "episodes", "win_rate", "policy_loss", "value_loss", "entropy")
 
 
 def run(name, **kw):
@@ -32,7 +32,7 @@ if __name__ == "__main__":
     if "--multi" in sys.argv:
         world = dist_env()[2]
         n = 131072 * world
-        run(f"vs_dummy_hard_{world}gpu_sharded", mode="vs_dummy", num_envs=n, total_steps=n * 16 * 2,
+        run(f"vs_dummy_hard_{world}gpu_sharded", mode="vs_dummy", num_envs=n, total_steps=n * 16 * 4,
             opponent_difficulty="hard", rollout_steps=16, batch_size=32768, epochs=1, precision="bf16")
         if torch.distributed.is_initialized():
             torch.distributed.destroy_process_group()
@@ -41,7 +41,7 @@ if __name__ == "__main__":
             opponent_difficulty="hard", precision="fp32", reference_gae=True)
         run("config0_vs_dummy_envs4_bf16", mode="vs_dummy", num_envs=4, total_steps=8192,
             opponent_difficulty="hard", precision="bf16")
-        run("vs_dummy_hard_envs65536_bf16", mode="vs_dummy", num_envs=65536, total_steps=65536 * 16 * 2,
+        run("vs_dummy_hard_envs65536_bf16", mode="vs_dummy", num_envs=65536, total_steps=65536 * 16 * 3,
             opponent_difficulty="hard", rollout_steps=16, batch_size=16384, precision="bf16")
-        run("config3_selfplay_envs65536_bf16", mode="selfplay", num_envs=65536, total_steps=65536 * 16 * 2,
+        run("config3_selfplay_envs65536_bf16", mode="selfplay", num_envs=65536, total_steps=65536 * 16 * 3,
             rollout_steps=16, batch_size=16384, precision="bf16")
