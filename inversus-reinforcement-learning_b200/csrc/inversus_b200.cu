@@ -530,6 +530,9 @@ int inv_step_host(inv_sim *s, const int8_t *a1, const int8_t *a2, void *obs_p1, 
     }
     DeviceGuard g(s->cfg.device);
     cudaStream_t st = s->host_stream;
+    // the *_host calls are synchronous: order them after whatever the caller enqueued on other
+    // streams for this handle (inv_step / inv_reset_envs on a torch stream, say)
+    CUDA_TRY(cudaDeviceSynchronize());
     // action ids travel host -> pinned staging -> device on the handle's own stream
     memcpy(s->h_a1, a1, (size_t)n);
     CUDA_TRY(cudaMemcpyAsync(s->d_a1, s->h_a1, (size_t)n, cudaMemcpyHostToDevice, st));
@@ -583,6 +586,7 @@ int inv_reset_host(inv_sim *s, void *obs_p1, float *extra_p1, void *obs_p2, floa
     if (obs_p2 && !s->obs2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
     DeviceGuard g(s->cfg.device);
     cudaStream_t st = s->host_stream;
+    CUDA_TRY(cudaDeviceSynchronize()); // see inv_step_host
     int rc = inv_reset(s, st);
     if (rc != INV_OK) return rc;
     rc = copy_small_outputs(s, st, extra_p1, extra_p2, nullptr, nullptr, nullptr, nullptr, nullptr);
