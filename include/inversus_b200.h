@@ -211,6 +211,21 @@ int inv_gae(const float *reward_dev, const float *value_dev, const uint8_t *done
             const float *last_value_dev, double gamma, double lam, int32_t T, int64_t N, float *adv_dev,
             float *ret_dev, void *stream);
 
+/* Fused LayerNorm(+residual)+ReLU of the policy's channels-last bf16 path (the memory-bound glue
+ * between the convolutions of inversus_rl/policies.py:27-45,94-100; the contractions themselves stay
+ * in cuDNN/cuBLAS). A sample is D = H*W*C contiguous bf16 values in HWC order, gamma/beta are [D]
+ * bf16 in the same order, statistics are fp32. res may be NULL. D % 8 == 0, D <= 20480.
+ *   fwd: y = relu(LN(x [+ res]) * gamma + beta); writes mean[B], rstd[B] for the backward.
+ *   bwd: dx (also the gradient of res), dgamma[D], dbeta[D] (fp32); partials is scratch of
+ *        inv_ln_relu_partials(D) * 2 * D floats. All pointers are device pointers on the current
+ *        device. */
+int inv_ln_relu_partials(int32_t D);
+int inv_ln_relu_fwd(const void *x, const void *res, const void *gamma, const void *beta, int64_t B, int32_t D,
+                    float eps, void *y, float *mean, float *rstd, void *stream);
+int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *gamma, const void *beta,
+                    const float *mean, const float *rstd, int64_t B, int32_t D, void *dx, float *dgamma,
+                    float *dbeta, float *partials, void *stream);
+
 /* kernel launches issued through this handle so far (bench.py's gpu_launches) */
 int64_t inv_launch_count(const inv_sim *sim);
 

@@ -1,0 +1,351 @@
+// policy_kernels.cu -- fused LayerNorm(+residual)+ReLU for the policy's channels-last bf16 path.
+//
+// The policy CNN (inversus_rl/policies.py:27-45, :94-100) applies LayerNorm over the whole
+// [C,H,W] feature map after every convolution, then ReLU (and a residual add before the fourth).
+// The contractions stay in cuDNN/cuBLAS; this file fuses the memory-bound glue between them:
+//
+//   forward   y = relu( LN(x [+ res]) * gamma + beta )          one read of x (and res), one write of y
+//   backward  dx = LN'(relu'(dy)) ; dgamma, dbeta               one read of dy, x (and res), one write of dx
+//
+// Layout: a sample is D = H*W*C contiguous bf16 values in HWC order (the memory of a
+// channels-last tensor); gamma/beta are [D] bf16 in the same order. Statistics and all arithmetic
+// are fp32. Both kernels are persistent: a CTA keeps its slice of gamma/beta in registers and
+// walks over samples, so the affine parameters are read once per CTA instead of once per sample.
+// The backward keeps per-CTA dgamma/dbeta accumulators in shared memory (2*D floats, up to 150 KB)
+// and writes them as partials that a second small kernel reduces -- deterministic, no atomics.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/inversus_b200.h"
+
+namespace {
+
+constexpr int kLnThreads = 512;
+
+__device__ __forceinline__ void unpack8(const uint4 &v, float (&f)[8])
+{
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8])
+{
+    uint4 v;
+    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return v;
+}
+
+// sum of (a, b) over the CTA; result broadcast to every thread
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2 *scratch)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads(); // scratch may still be read from the previous call
+    if (lane == 0) scratch[warp] = make_float2(a, b);
+    __syncthreads();
+    float2 t = lane < (kLnThreads / 32) ? scratch[lane] : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
+        t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+    }
+    return make_float2(__shfl_sync(0xffffffffu, t.x, 0), __shfl_sync(0xffffffffu, t.y, 0));
+}
+
+// Two CTAs per SM (<= 64 registers at 512 threads): while one CTA sits in its block reduction the
+// other streams. gamma/beta are cached in registers only for the narrow layers (MAXV <= 2); the
+// wide ones re-read them per sample from L1/L2.
+template <int MAXV, bool HAS_RES>
+__global__ void __launch_bounds__(kLnThreads, 2)
+ln_relu_fwd_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ res, const uint4 *__restrict__ gamma,
+                   const uint4 *__restrict__ beta, int64_t B, int nvec, float eps, uint4 *__restrict__ y,
+                   float *__restrict__ mean_out, float *__restrict__ rstd_out)
+{
+    __shared__ float2 scratch[kLnThreads / 32];
+    const int tid = threadIdx.x;
+    constexpr bool kCacheGB = MAXV <= 2;
+    uint4 g[kCacheGB ? MAXV : 1], bt[kCacheGB ? MAXV : 1];
+    if (kCacheGB) {
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int i = k * kLnThreads + tid;
+            if (i < nvec) { g[k] = gamma[i]; bt[k] = beta[i]; }
+        }
+    }
+    const float inv_d = 1.0f / (float)(nvec * 8);
+    for (int64_t s = blockIdx.x; s < B; s += gridDim.x) {
+        const uint4 *xs = x + s * nvec;
+        uint4 xv[MAXV], rv[HAS_RES ? MAXV : 1]; // inputs stay packed (bf16) between the two passes
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int i = k * kLnThreads + tid;
+            if (i < nvec) {
+                xv[k] = xs[i];
+                if (HAS_RES) rv[k] = res[s * nvec + i];
+            }
+        }
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int i = k * kLnThreads + tid;
+            if (i < nvec) {
+                float z[8];
+                unpack8(xv[k], z);
+                if (HAS_RES) {
+                    float r[8];
+                    unpack8(rv[k], r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] += r[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { sum += z[j]; sq += z[j] * z[j]; }
+            }
+        }
+        const float2 t = block_sum2(sum, sq, scratch);
+        const float mean = t.x * inv_d;
+        const float var = fmaxf(t.y * inv_d - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        if (tid == 0) { mean_out[s] = mean; rstd_out[s] = rstd; }
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int i = k * kLnThreads + tid;
+            if (i < nvec) {
+                float z[8], gf[8], bf[8], o[8];
+                unpack8(xv[k], z);
+                if (HAS_RES) {
+                    float r[8];
+                    unpack8(rv[k], r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] += r[j];
+                }
+                unpack8(kCacheGB ? g[k] : gamma[i], gf);
+                unpack8(kCacheGB ? bt[k] : beta[i], bf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = fmaxf((z[j] - mean) * rstd * gf[j] + bf[j], 0.f);
+                y[s * nvec + i] = pack8(o);
+            }
+        }
+    }
+}
+
+// dynamic smem: float acc[2][nvec*8]  (dgamma, dbeta of this CTA)
+template <int MAXV, bool HAS_RES>
+__global__ void __launch_bounds__(kLnThreads)
+ln_relu_bwd_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, const uint4 *__restrict__ res,
+                   const uint4 *__restrict__ gamma, const uint4 *__restrict__ beta, const float *__restrict__ mean_in,
+                   const float *__restrict__ rstd_in, int64_t B, int nvec, uint4 *__restrict__ dx,
+                   float *__restrict__ partials)
+{
+    extern __shared__ float acc[];
+    __shared__ float2 scratch[kLnThreads / 32];
+    const int tid = threadIdx.x;
+    const int D = nvec * 8;
+    for (int i = tid; i < 2 * D; i += kLnThreads) acc[i] = 0.f;
+    __syncthreads();
+    // gamma/beta live in registers across samples when the slice is small; for the two 19200-wide
+    // layers (MAXV >= 4) that would spill, so they are re-read per sample (they stay L1/L2-resident)
+    constexpr bool kCacheGB = MAXV <= 3;
+    uint4 g[kCacheGB ? MAXV : 1], bt[kCacheGB ? MAXV : 1];
+    if (kCacheGB) {
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int i = k * kLnThreads + tid;
+            if (i < nvec) { g[k] = gamma[i]; bt[k] = beta[i]; }
+        }
+    }
+    const float inv_d = 1.0f / (float)D;
+    // from here on each thread only touches its own accumulator slots: no barrier needed around acc
+    for (int64_t s = blockIdx.x; s < B; s += gridDim.x) {
+        const float mean = mean_in[s], rstd = rstd_in[s];
+        // issue every global load of this sample before touching the data (memory-level
+        // parallelism); the packed inputs stay in registers for both passes
+        uint4 xv[MAXV], dv[MAXV], rv[HAS_RES ? MAXV : 1];
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int i = k * kLnThreads + tid;
+            if (i < nvec) {
+                xv[k] = x[s * nvec + i];
+                dv[k] = dy[s * nvec + i];
+                if (HAS_RES) rv[k] = res[s * nvec + i];
+            }
+        }
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int i = k * kLnThreads + tid;
+            if (i < nvec) {
+                float z[8], d[8], gf[8], bf[8];
+                unpack8(xv[k], z);
+                if (HAS_RES) {
+                    float r[8];
+                    unpack8(rv[k], r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] += r[j];
+                }
+                unpack8(dv[k], d);
+                unpack8(kCacheGB ? g[k] : gamma[i], gf);
+                unpack8(kCacheGB ? bt[k] : beta[i], bf);
+                // accumulators are element-major (acc[j*nvec + i]) so that the 32 lanes of a warp
+                // hit 32 different banks; i*8 + j would be an 8-way conflict on every access
+                float *ag = acc + i, *ab = acc + D + i;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float h = (z[j] - mean) * rstd;
+                    const float gy = (h * gf[j] + bf[j] > 0.f) ? d[j] : 0.f; // relu'
+                    ag[j * nvec] += gy * h;
+                    ab[j * nvec] += gy;
+                    const float w = gy * gf[j];
+                    s1 += w;
+                    s2 += w * h;
+                }
+            }
+        }
+        const float2 t = block_sum2(s1, s2, scratch);
+        const float m1 = t.x * inv_d, m2 = t.y * inv_d;
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            const int i = k * kLnThreads + tid;
+            if (i < nvec) {
+                float z[8], d[8], gf[8], bf[8], o[8];
+                unpack8(xv[k], z);
+                if (HAS_RES) {
+                    float r[8];
+                    unpack8(rv[k], r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] += r[j];
+                }
+                unpack8(dv[k], d);
+                unpack8(kCacheGB ? g[k] : gamma[i], gf);
+                unpack8(kCacheGB ? bt[k] : beta[i], bf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float h = (z[j] - mean) * rstd;
+                    const float w = (h * gf[j] + bf[j] > 0.f) ? d[j] * gf[j] : 0.f;
+                    o[j] = rstd * (w - m1 - h * m2);
+                }
+                dx[s * nvec + i] = pack8(o);
+            }
+        }
+    }
+    float *out = partials + (size_t)blockIdx.x * 2 * D;
+    for (int k = 0; k < MAXV; ++k) {
+        const int i = k * kLnThreads + tid;
+        if (i < nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                out[i * 8 + j] = acc[j * nvec + i];
+                out[D + i * 8 + j] = acc[D + j * nvec + i];
+            }
+        }
+    }
+}
+
+__global__ void reduce_partials_kernel(const float *__restrict__ partials, int nparts, int n2d,
+                                       float *__restrict__ dgamma, float *__restrict__ dbeta, int D)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2d) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * n2d + i];
+    if (i < D) dgamma[i] = s;
+    else dbeta[i - D] = s;
+}
+
+int sm_count_cached()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+} // namespace
+
+extern "C" {
+
+int inv_ln_relu_partials(int32_t D) { (void)D; return sm_count_cached(); }
+
+int inv_ln_relu_fwd(const void *x, const void *res, const void *gamma, const void *beta, int64_t B, int32_t D,
+                    float eps, void *y, float *mean, float *rstd, void *stream)
+{
+    if (!x || !gamma || !beta || !y || !mean || !rstd || B < 0 || D <= 0 || D % 8) return INV_ERR_INVALID_ARG;
+    if (B == 0) return INV_OK;
+    const int nvec = D / 8;
+    const int maxv = (nvec + kLnThreads - 1) / kLnThreads;
+    if (maxv > 5) return INV_ERR_INVALID_ARG; // D <= 20480
+    const int64_t cap = (int64_t)sm_count_cached() * 4;
+    const unsigned grid = (unsigned)(B < cap ? B : cap);
+    cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(MV)                                                                                              \
+    if (res)                                                                                                    \
+        ln_relu_fwd_kernel<MV, true><<<grid, kLnThreads, 0, st>>>((const uint4 *)x, (const uint4 *)res,         \
+            (const uint4 *)gamma, (const uint4 *)beta, B, nvec, eps, (uint4 *)y, mean, rstd);                    \
+    else                                                                                                        \
+        ln_relu_fwd_kernel<MV, false><<<grid, kLnThreads, 0, st>>>((const uint4 *)x, nullptr,                   \
+            (const uint4 *)gamma, (const uint4 *)beta, B, nvec, eps, (uint4 *)y, mean, rstd);
+    switch (maxv) {
+    case 1: LAUNCH(1) break;
+    case 2: LAUNCH(2) break;
+    case 3: LAUNCH(3) break;
+    case 4: LAUNCH(4) break;
+    default: LAUNCH(5) break;
+    }
+#undef LAUNCH
+    return cudaGetLastError() == cudaSuccess ? INV_OK : INV_ERR_CUDA;
+}
+
+int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *gamma, const void *beta,
+                    const float *mean, const float *rstd, int64_t B, int32_t D, void *dx, float *dgamma,
+                    float *dbeta, float *partials, void *stream)
+{
+    if (!dy || !x || !gamma || !beta || !mean || !rstd || !dx || !dgamma || !dbeta || !partials || B <= 0 ||
+        D <= 0 || D % 8)
+        return INV_ERR_INVALID_ARG;
+    const int nvec = D / 8;
+    const int maxv = (nvec + kLnThreads - 1) / kLnThreads;
+    if (maxv > 5) return INV_ERR_INVALID_ARG;
+    const int nsm = sm_count_cached();
+    const unsigned grid = (unsigned)(B < nsm ? B : nsm); // one CTA per SM: 2*D floats of shared memory each
+    const size_t smem = (size_t)2 * D * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(MV)                                                                                              \
+    if (res) {                                                                                                  \
+        cudaFuncSetAttribute(ln_relu_bwd_kernel<MV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        ln_relu_bwd_kernel<MV, true><<<grid, kLnThreads, smem, st>>>((const uint4 *)dy, (const uint4 *)x,       \
+            (const uint4 *)res, (const uint4 *)gamma, (const uint4 *)beta, mean, rstd, B, nvec, (uint4 *)dx,     \
+            partials);                                                                                          \
+    } else {                                                                                                    \
+        cudaFuncSetAttribute(ln_relu_bwd_kernel<MV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        ln_relu_bwd_kernel<MV, false><<<grid, kLnThreads, smem, st>>>((const uint4 *)dy, (const uint4 *)x,      \
+            nullptr, (const uint4 *)gamma, (const uint4 *)beta, mean, rstd, B, nvec, (uint4 *)dx, partials);     \
+    }
+    switch (maxv) {
+    case 1: LAUNCH(1) break;
+    case 2: LAUNCH(2) break;
+    case 3: LAUNCH(3) break;
+    case 4: LAUNCH(4) break;
+    default: LAUNCH(5) break;
+    }
+#undef LAUNCH
+    if (cudaGetLastError() != cudaSuccess) return INV_ERR_CUDA;
+    const int n2d = 2 * D;
+    reduce_partials_kernel<<<(n2d + 255) / 256, 256, 0, st>>>(partials, (int)grid, n2d, dgamma, dbeta, D);
+    return cudaGetLastError() == cudaSuccess ? INV_OK : INV_ERR_CUDA;
+}
+
+} // extern "C"

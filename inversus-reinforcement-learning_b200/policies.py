@@ -40,6 +40,7 @@ class InversusCNNPolicy(nn.Module):
         self.relu = nn.ReLU()
         self.flatten = nn.Flatten()
         self.feature_dim = _CONV_WIDTHS[-1] * height * width
+        self.use_fused_kernels = True  # CUDA only: fused LayerNorm(+residual)+ReLU kernels in forward_bf16
         self.fc_actor = _mlp_head(self.feature_dim + extra_dim, hidden_dim, NUM_ACTIONS)
         self.fc_critic = _mlp_head(self.feature_dim + extra_dim, hidden_dim, 1)
 
@@ -89,17 +90,27 @@ class InversusCNNPolicy(nn.Module):
         bf = torch.bfloat16
         H, W = self.height, self.width
         x = grid_tensor.to(bf).contiguous(memory_format=torch.channels_last)
+        nb = x.shape[0]
+        fused = x.is_cuda and self.use_fused_kernels
         res = None
         for i in (1, 2, 3, 4):
             y = F.conv2d(x, prep[f"cw{i}"], prep[f"cb{i}"], padding=1)
-            if i == 4:
-                y = y + res                                      # residual around conv4 (policies.py:98-100)
+            eps = getattr(self, f"norm{i}").eps
             yp = y.permute(0, 2, 3, 1)                           # [B,H,W,C] view of channels-last memory
-            yp = F.layer_norm(yp, (H, W, yp.shape[-1]), prep[f"nw{i}"], prep[f"nb{i}"], getattr(self, f"norm{i}").eps)
-            x = F.relu(yp).permute(0, 3, 1, 2)                   # back to an NCHW view, still channels-last
+            c = yp.shape[-1]
+            if fused:  # one hand-written kernel: (+residual) -> LayerNorm -> affine -> ReLU (csrc/policy_kernels.cu)
+                from .fused_ops import layer_norm_relu
+                flat = layer_norm_relu(yp.reshape(nb, -1), prep[f"nw{i}"].reshape(-1), prep[f"nb{i}"].reshape(-1), eps,
+                                       residual=res.permute(0, 2, 3, 1).reshape(nb, -1) if i == 4 else None)
+                x = flat.view(nb, H, W, c).permute(0, 3, 1, 2)
+            else:
+                if i == 4:
+                    yp = yp + res.permute(0, 2, 3, 1)            # residual around conv4 (policies.py:98-100)
+                yp = F.layer_norm(yp, (H, W, c), prep[f"nw{i}"], prep[f"nb{i}"], eps)
+                x = F.relu(yp).permute(0, 3, 1, 2)               # back to an NCHW view, still channels-last
             if i == 3:
                 res = x
-        feat = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)     # [B, H*W*C] without a copy
+        feat = x.permute(0, 2, 3, 1).reshape(nb, -1)             # [B, H*W*C] without a copy
         ex = F.pad(extra_vector.to(bf), (0, prep["w_extra"].shape[1] - self.extra_dim))
         h = F.relu(F.linear(feat, prep["w_feat"], prep["b0"]) + F.linear(ex, prep["w_extra"]))
         n_a = self.fc_actor[0].out_features

@@ -116,3 +116,64 @@ def test_ppo_learns_to_beat_the_easy_dummy():
     print("control:", base["wins_per_kstep"], base["last_window"], "trained:", out["wins_per_kstep"], out["last_window"],
           {k: out[k] for k in ("samples_per_s", "rollout_s", "update_s", "rollout_env_steps_per_s")})
     assert out["wins_per_kstep"] > 1.5 * base["wins_per_kstep"], (base, out)
+
+
+def test_fused_layernorm_relu_kernels_match_torch():
+    """csrc/policy_kernels.cu vs the plain PyTorch fp32 reference of the same op, for the three
+    layer widths of the policy (D = 4800, 9600, 19200), with and without the residual input.
+    Tolerances: forward 2e-2 relative to the output range (bf16 output, 8-bit mantissa); dx cosine
+    > 0.999 and max error < 2 % of its max magnitude; dgamma/dbeta (fp32 accumulation, compared
+    after their bf16 rounding) within 2 % of max."""
+    import torch
+    import torch.nn.functional as F
+    from inversus_b200.fused_ops import layer_norm_relu
+    torch.manual_seed(0)
+    for D in (4800, 9600, 19200):
+        for with_res in (False, True):
+            for B in (3, 700):
+                x = torch.randn(B, D, device="cuda").to(torch.bfloat16).requires_grad_()
+                r = torch.randn(B, D, device="cuda").to(torch.bfloat16).requires_grad_() if with_res else None
+                g = (torch.rand(D, device="cuda") + 0.5).to(torch.bfloat16).requires_grad_()
+                b = (torch.rand(D, device="cuda") - 0.5).to(torch.bfloat16).requires_grad_()
+                dy = torch.randn(B, D, device="cuda").to(torch.bfloat16)
+                y = layer_norm_relu(x, g, b, 1e-5, residual=r)
+                y.backward(dy)
+                xf = x.detach().float().requires_grad_()
+                rf = r.detach().float().requires_grad_() if with_res else None
+                gf, bf_ = g.detach().float().requires_grad_(), b.detach().float().requires_grad_()
+                z = xf + rf if with_res else xf
+                yr = F.relu(F.layer_norm(z, (D,), gf, bf_, 1e-5))
+                yr.backward(dy.float())
+                assert (y.float() - yr).abs().max() < 2e-2 * max(1.0, yr.abs().max().item())
+                pairs = [(x.grad, xf.grad), (g.grad, gf.grad), (b.grad, bf_.grad)]
+                if with_res:
+                    pairs.append((r.grad, rf.grad))
+                for got, want in pairs:
+                    got = got.float()
+                    assert F.cosine_similarity(got.flatten(), want.flatten(), dim=0) > 0.999
+                    assert (got - want).abs().max() <= 0.02 * want.abs().max() + 1e-3, (D, with_res, B)
+
+
+def test_fused_policy_path_matches_unfused():
+    import torch
+    from inversus_b200.policies import InversusCNNPolicy
+    torch.manual_seed(0)
+    m = InversusCNNPolicy().cuda()
+    for i in (1, 2, 3, 4):
+        n = getattr(m, f"norm{i}")
+        n.weight.data.uniform_(0.5, 1.5)
+        n.bias.data.uniform_(-0.5, 0.5)
+    g = (torch.rand(256, 12, 10, 15, device="cuda") > 0.7)
+    e = torch.rand(256, 4, device="cuda")
+    outs, grads = [], []
+    for fused in (True, False):
+        m.use_fused_kernels = fused
+        m.zero_grad()
+        lo, va = m.forward_bf16(g, e)
+        (lo.sum() + va.sum()).backward()
+        outs.append((lo.detach(), va.detach()))
+        grads.append([p.grad.clone() for p in m.parameters()])
+    assert (outs[0][0] - outs[1][0]).abs().max() < 3e-2 and (outs[0][1] - outs[1][1]).abs().max() < 3e-2
+    for (name, _), a, b in zip(m.named_parameters(), *grads):
+        cs = torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0)
+        assert cs > 0.99, (name, cs.item())
