@@ -377,9 +377,36 @@ def main():
             torch.cuda.synchronize()
             pl, tot = time_steps(s2, torch, a, a2, 200)
             bts = constants.algorithmic_bytes_per_env_step(elem, selfplay) * ns
+            # the same 16 steps captured once in a CUDA graph and replayed: launch overhead of the
+            # Python/ctypes call path removed (what a graph-captured rollout loop would see)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for k in range(N_ACTION_SETS):
+                    s2.step(a[k], None if a2 is None else a2[k])
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for k in range(N_ACTION_SETS):
+                    s2.step(a[k], None if a2 is None else a2[k])
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(1, 400 // N_ACTION_SETS)
+            e0.record()
+            for _ in range(reps):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            gms = e0.elapsed_time(e1) / (reps * N_ACTION_SETS)
             print(json.dumps({"sweep_envs": ns, "env_steps_per_sec": ns * 200 / (tot * 1e-3),
                               "ms_per_step": tot / 200, "hbm_gbs": bts / (tot / 200 * 1e-3) / 1e9,
-                              "frac_of_peak": bts / (tot / 200 * 1e-3) / 1e9 / peak}), file=sys.stderr, flush=True)
+                              "frac_of_peak": bts / (tot / 200 * 1e-3) / 1e9 / peak,
+                              "cuda_graph": {"ms_per_step": gms, "env_steps_per_sec": ns / (gms * 1e-3),
+                                             "frac_of_peak": bts / (gms * 1e-3) / 1e9 / peak}}),
+                  file=sys.stderr, flush=True)
+            del graph
             s2.close()
             del s2, a, a2
 
