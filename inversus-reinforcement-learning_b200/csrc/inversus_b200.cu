@@ -139,11 +139,13 @@ Params base_params(const inv_sim *s)
     return p;
 }
 
-// Launch shape (measured, profiles/r1_tile_grid_sweep.txt): a tile of 32 envs per 128-thread CTA --
-// one warp runs the game logic, all four stream the observations -- and ONE CTA PER TILE. Letting
-// the hardware block scheduler hand out tiles keeps CTAs desynchronised, so logic phases of some
-// overlap store phases of others: 0.99 of the measured HBM peak at 1M-4M envs, versus 0.94 for a
-// persistent grid-stride loop (whose CTAs drift into lock-step) and 0.96 for 128-env tiles.
+// Launch shape (measured, profiles/r1_tile_grid_sweep.txt): 128-thread CTAs, a tile of E envs per
+// CTA (E/32 warps run the game logic, all four stream the observations) and ONE CTA PER TILE.
+// Letting the hardware block scheduler hand out tiles keeps CTAs desynchronised, so logic phases
+// of some overlap store phases of others: 0.99 of the measured HBM peak at 1M-4M envs for fp32
+// observations with E = 32, versus 0.94 for a persistent grid-stride loop (whose CTAs drift into
+// lock-step). The narrower the observation, the more logic per stored byte, so bf16/u8 step
+// kernels use more logic warps per CTA: E = 64 (bf16, one view) or 128 (bf16 two views, u8).
 constexpr int kTileEnvs = 32;
 
 template <int OP, int DT, bool P2V, bool INDEXED, int E>
@@ -168,7 +170,12 @@ cudaError_t launch_one(const Params &p, int sm_count, cudaStream_t st)
 template <int OP, int DT, bool P2V, bool INDEXED>
 cudaError_t launch_e(const Params &p, int sm_count, cudaStream_t st)
 {
-    return launch_one<OP, DT, P2V, INDEXED, kTileEnvs>(p, sm_count, st);
+    if constexpr (OP == OP_STEP && !INDEXED && DT != INV_OBS_F32) {
+        constexpr int E = (DT == INV_OBS_BF16 && !P2V) ? 64 : 128;
+        return launch_one<OP_STEP, DT, P2V, false, E>(p, sm_count, st);
+    } else {
+        return launch_one<OP, DT, P2V, INDEXED, kTileEnvs>(p, sm_count, st);
+    }
 }
 
 template <int OP, bool INDEXED>
