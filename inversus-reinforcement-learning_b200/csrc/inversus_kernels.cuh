@@ -45,6 +45,20 @@ constexpr uint32_t kThreshMoveEasy = 4294968u;       // !(u > 0.001)
 
 enum : int { OP_STEP = 0, OP_RESET = 1, OP_OBS = 2, OP_DEBUG = 3 };
 
+// Exact binary64 values of the proximity term 0.002 * (1.0 - dist / 25) (env_wrappers.py:378-382)
+// for dist = 0..23, and exact binary32 values of (float)(ammo / 6) (env_wrappers.py:238-240):
+// computed with the reference's own arithmetic (Python floats / numpy.float32) and written as hex
+// literals, so the kernel needs no fp64 division. tests/test_rng_spec.py re-derives both tables.
+__constant__ double kProximity[24] = {
+    0x1.0624dd2f1a9fcp-9,  0x1.f75104d551d69p-10, 0x1.e2584f4c6e6dap-10, 0x1.cd5f99c38b04bp-10,
+    0x1.b866e43aa79bcp-10, 0x1.a36e2eb1c432dp-10, 0x1.8e757928e0c9ep-10, 0x1.797cc39ffd60ep-10,
+    0x1.64840e1719f7fp-10, 0x1.4f8b588e368f1p-10, 0x1.3a92a30553261p-10, 0x1.2599ed7c6fbd3p-10,
+    0x1.10a137f38c544p-10, 0x1.f75104d551d69p-11, 0x1.cd5f99c38b04ap-11, 0x1.a36e2eb1c432dp-11,
+    0x1.797cc39ffd60ep-11, 0x1.4f8b588e368f0p-11, 0x1.2599ed7c6fbd3p-11, 0x1.f75104d551d69p-12,
+    0x1.a36e2eb1c432bp-12, 0x1.4f8b588e368f2p-12, 0x1.f75104d551d69p-13, 0x1.4f8b588e368eep-13};
+__constant__ float kAmmoNorm[8] = {0x0.0p+0f, 0x1.555556p-3f, 0x1.555556p-2f, 0x1.0p-1f,
+                                   0x1.555556p-1f, 0x1.aaaaaap-1f, 0x1.0p+0f, 0x1.2aaaaap+0f};
+
 struct Params {
     uint4 *state;            // [5][stride] packed planes (read/write)
     const uint4 *state_in;   // OP_OBS: snapshot planes (read only)
@@ -154,8 +168,10 @@ __device__ __forceinline__ void load_env(Env &s, uint16_t *sb, const uint4 *st, 
     const uint32_t w[8] = {d.x, d.y, d.z, d.w, e.x, e.y, e.z, e.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        sb[(2 * k) * E] = (uint16_t)(w[k] & 0xFFFFu);
-        sb[(2 * k + 1) * E] = (uint16_t)(w[k] >> 16);
+        if (2 * k < s.nb) { // slots >= nb hold zeros and are never read
+            sb[(2 * k) * E] = (uint16_t)(w[k] & 0xFFFFu);
+            sb[(2 * k + 1) * E] = (uint16_t)(w[k] >> 16);
+        }
     }
 }
 
@@ -438,10 +454,7 @@ __device__ __forceinline__ int dummy_policy(const Env &s, Draws &dr, int difficu
 }
 
 // (float)(k / 6.0) for the extra vector (env_wrappers.py:238-243)
-__device__ __forceinline__ float ammo_norm(int k)
-{
-    return __double2float_rn(__ddiv_rn((double)k, 6.0));
-}
+__device__ __forceinline__ float ammo_norm(int k) { return kAmmoNorm[k & 7]; }
 __device__ __forceinline__ float4 extra_vec(const Env &s, int viewer)
 {
     const int e = 1 - viewer;
@@ -577,8 +590,7 @@ __global__ void __launch_bounds__(kThreads) inv_kernel(const Params p)
                 if (s.alive[0] && s.ammo[0] == 0) r = __dadd_rn(r, -0.001);                        // :372-373
                 if (s.alive[0] && s.alive[1]) {                                                    // :377-405
                     const int dist = abs(s.x[0] - s.x[1]) + abs(s.y[0] - s.y[1]);
-                    const double frac = __ddiv_rn((double)dist, (double)(kW + kH));
-                    r = __dadd_rn(r, __dmul_rn(0.002, __dsub_rn(1.0, frac)));
+                    r = __dadd_rn(r, kProximity[dist]); // 0.002 * (1 - dist / 25), dist <= 23
                     const bool aligned = (s.x[0] == s.x[1]) || (s.y[0] == s.y[1]);
                     if (aligned) r = __dadd_rn(r, 0.002);
                     if (a1 >= 5 && aligned && s.ammo[0] > 0) {

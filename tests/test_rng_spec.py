@@ -55,3 +55,22 @@ def test_integer_thresholds_equal_the_float_comparisons():
     T = th.THRESH_MOVE_EASY
     for r in range(T - 3, T + 3):
         assert ((r / 4294967296.0) > 0.001) == (not r < T)
+
+
+def test_kernel_lookup_tables_are_the_reference_arithmetic():
+    """The fp64 proximity table and the fp32 ammo table in the CUDA source are exactly what the
+    reference's Python expressions evaluate to (env_wrappers.py:378-382 and :238-240)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cu = open(os.path.join(root, "inversus-reinforcement-learning_b200", "csrc", "inversus_kernels.cuh")).read()
+    prox = re.search(r"kProximity\[24\] = \{(.*?)\};", cu, re.S).group(1)
+    vals = [float.fromhex(v.strip()) for v in prox.replace("\n", " ").split(",")]
+    assert len(vals) == 24
+    for dist, v in enumerate(vals):
+        assert v == 0.002 * (1.0 - dist / 25), dist  # max_dist = width + height = 25
+    ammo = re.search(r"kAmmoNorm\[8\] = \{(.*?)\};", cu, re.S).group(1)
+    avals = [float.fromhex(v.strip().rstrip("f")) for v in ammo.replace("\n", " ").split(",")]
+    for k in range(7):  # MAX_AMMO = 6
+        assert np.float32(avals[k]) == np.float32(k / 6), k
+        assert float(np.float32(avals[k])) == avals[k]
