@@ -148,11 +148,11 @@ Params base_params(const inv_sim *s)
 // kernels use more logic warps per CTA: E = 64 (bf16, one view) or 128 (bf16 two views, u8).
 constexpr int kTileEnvs = 32;
 
-template <int OP, int DT, bool P2V, bool INDEXED, int E>
+template <int OP, int DT, bool P2V, bool INDEXED, int E, int T = kThreads>
 cudaError_t launch_one(const Params &p, int sm_count, cudaStream_t st)
 {
     (void)sm_count;
-    auto kern = inv_kernel<OP, DT, P2V, INDEXED, E>;
+    auto kern = inv_kernel<OP, DT, P2V, INDEXED, E, T>;
     constexpr size_t smem = smem_bytes<E, P2V, INDEXED>();
     static bool configured = false; // per instantiation
     if (!configured) {
@@ -163,7 +163,7 @@ cudaError_t launch_one(const Params &p, int sm_count, cudaStream_t st)
     const int64_t ntiles = (p.count + E - 1) / E;
     if (ntiles <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)(ntiles < (int64_t)0x7FFFFFFF ? ntiles : (int64_t)0x7FFFFFFF);
-    kern<<<grid, kThreads, smem, st>>>(p);
+    kern<<<grid, T, smem, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -532,10 +532,10 @@ constexpr size_t smem_bytes()
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int OP, int DT, bool P2V, bool INDEXED, int E>
-__global__ void __launch_bounds__(kThreads) inv_kernel(const Params p)
+template <int OP, int DT, bool P2V, bool INDEXED, int E, int T = kThreads>
+__global__ void __launch_bounds__(T) inv_kernel(const Params p)
 {
-    static_assert(E <= kThreads && E % 32 == 0, "tile must be whole warps");
+    static_assert(E <= T && E % 32 == 0 && T % 32 == 0, "tile must be whole warps");
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *rows1 = smem;
     uint32_t *rows2 = rows1 + (P2V ? E * kRowWords : 0);
@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(kThreads) inv_kernel(const Params p)
             if (!INDEXED) {
                 chunk_t *o = out + base * Fmt::kChunks;
 #pragma unroll 4
-                for (int g = tid; g < total; g += kThreads) {
+                for (int g = tid; g < total; g += T) {
                     const int e = g / Fmt::kChunks;
                     const int bit = (g - e * Fmt::kChunks) * Fmt::kBits;
                     const uint32_t w = rows[e * kRowWords + (bit >> 5)] >> (bit & 31);
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(kThreads) inv_kernel(const Params p)
                 }
             } else {
 #pragma unroll 2
-                for (int g = tid; g < total; g += kThreads) {
+                for (int g = tid; g < total; g += T) {
                     const int e = g / Fmt::kChunks;
                     const int c = g - e * Fmt::kChunks;
                     const int bit = c * Fmt::kBits;
@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(kThreads) inv_kernel(const Params p)
                 const uint32_t *rows = v ? rows2 : rows1;
                 uint4 *out = v ? p.bits2 : p.bits1;
                 if (!out) continue;
-                for (int g = tid; g < nvalid * 16; g += kThreads) {
+                for (int g = tid; g < nvalid * 16; g += T) {
                     const int e = g >> 4, c = g & 15;
                     const uint32_t *r = rows + e * kRowWords + 4 * c;
                     uint4 w;
