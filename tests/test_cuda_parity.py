@@ -186,3 +186,62 @@ def test_host_buffer_paths_deliver_identical_observations(mode):
                 assert np.array_equal(out[k], ref[k]), (name, k)
     assert sims["hybrid"][0].host_path()["dma_fraction"] == 0.5
     assert 0.0 <= sims["auto"][0].host_path()["dma_fraction"] <= 0.9
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "u8"])
+def test_indexed_reset_for_every_observation_dtype(dtype):
+    """MultiEnvRunner.envs[i].reset() path (inv_reset_envs) for all obs dtypes and both views:
+    only the listed envs change, and what they become equals a handle that reset them all."""
+    import torch
+    from inversus_b200 import BatchedInversus
+    n = 500
+    a = BatchedInversus(n, "selfplay", "hard", 50, seed=12, obs_dtype=dtype, auto_reset=False)
+    a.reset()
+    rs = np.random.RandomState(0)
+    for _ in range(10):
+        a.step(torch.from_numpy(rs.randint(0, 13, n).astype(np.int8)).cuda(),
+               torch.from_numpy(rs.randint(0, 13, n).astype(np.int8)).cuda())
+    before = a.export_state()
+    obs_before, obs2_before = a.obs.clone(), a.obs_p2.clone()
+    idx = np.array(sorted(rs.choice(n, 77, replace=False)))
+    a.reset_envs(idx)
+    after = a.export_state()
+    keep = np.setdiff1d(np.arange(n), idx)
+    for f in before.dtype.names:
+        assert np.array_equal(before[f][keep], after[f][keep]), f
+    assert torch.equal(a.obs[keep], obs_before[keep]) and torch.equal(a.obs_p2[keep], obs2_before[keep])
+    assert (after["episode"][idx] == 1).all() and (after["step_count"][idx] == 0).all()
+    assert (after["n_bullets"][idx] == 0).all() and (after["episode_return"][idx] == 0).all()
+    # the reset envs' observations equal a rebuild from their new state, in this dtype, for both views
+    snap = a.snapshot()
+    for view, got in ((0, a.obs), (1, a.obs_p2)):
+        want, _ = a.obs_from_packed(snap, view=view, obs_dtype=dtype)
+        assert torch.equal(got[idx].float(), want[idx].float())
+
+
+def test_state_import_export_roundtrip_and_validation():
+    from inversus_b200 import BatchedInversus
+    s = BatchedInversus(64, "dummy", "hard", 500, seed=1)
+    s.reset()
+    st = s.export_state()
+    st["bullets"][3, :2] = [[4, 5, 1, 0], [9, 2, 3, 1]]
+    st["n_bullets"][3] = 2
+    st["episode_return"][3] = -1.2345678901234567
+    st["p1"][3] = (14, 9, 0, 29, 0)
+    s.import_state(st[3:4], first=10)
+    back = s.export_state(10, 1)
+    for f in st.dtype.names:
+        assert np.array_equal(back[f][0], st[f][3]), f
+    for field, bad in (("p1", (15, 0, 0, 0, 1)), ("p2", (0, 10, 0, 0, 1)), ("p1", (0, 0, 8, 0, 1)), ("p1", (0, 0, 0, 0, 2))):
+        x = st[:1].copy()
+        x[field][0] = bad
+        with pytest.raises(ValueError):
+            s.import_state(x)
+    x = st[:1].copy()
+    x["n_bullets"][0] = 17
+    with pytest.raises(ValueError):
+        s.import_state(x)
+    x = st[:1].copy()
+    x["tiles"][0][4] = 1 << 22  # bit beyond the 150 tiles
+    with pytest.raises(ValueError):
+        s.import_state(x)
