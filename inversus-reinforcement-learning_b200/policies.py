@@ -134,12 +134,24 @@ class InversusCNNPolicy(nn.Module):
     def infer(self, grid_tensor: torch.Tensor, extra_vector: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """Rollout inference (no grad) through the bf16 path. The prepared bf16 weights are cached
         and rebuilt only when a parameter changed (optimizer steps bump tensor versions)."""
+        return self._forward_prepared(self.inference_weights(), grid_tensor, extra_vector)
+
+    @torch.no_grad()
+    def inference_weights(self) -> dict:
+        """The cached bf16 working copies used by `infer`. When a parameter changed they are
+        refreshed IN PLACE (same tensors, same addresses), so a CUDA graph that captured `infer`
+        keeps seeing current weights after an optimizer step."""
         key = tuple(p._version for p in self.parameters()) + (str(self.conv1.weight.device),)
         cache = getattr(self, "_infer_cache", None)
-        if cache is None or cache[0] != key:
-            cache = (key, self._prepare_bf16())
+        if cache is None or cache[0][-1] != key[-1]:
+            cache = [key, self._prepare_bf16()]
             object.__setattr__(self, "_infer_cache", cache)
-        return self._forward_prepared(cache[1], grid_tensor, extra_vector)
+        elif cache[0] != key:
+            fresh = self._prepare_bf16()
+            for k, v in cache[1].items():
+                v.copy_(fresh[k])
+            cache[0] = key
+        return cache[1]
 
 
 def make_policy_from_env(env=None) -> InversusCNNPolicy:

@@ -112,6 +112,19 @@ class DeviceRollout:
         self.dones[self.t].copy_(dones)
         self.t += 1
 
+    # CUDA-graph friendly variants: the time index lives on the device (a 1-element int64 tensor
+    # that the captured graph increments), so one captured step can be replayed T times.
+    def store_pre_at(self, t_dev: torch.Tensor, sim, actions, log_probs, values):
+        assert self.store == "packed"
+        self.packed.index_copy_(1, t_dev, sim.packed_state.unsqueeze(1))
+        self.actions.index_copy_(0, t_dev, actions.unsqueeze(0))
+        self.log_probs.index_copy_(0, t_dev, log_probs.unsqueeze(0))
+        self.values.index_copy_(0, t_dev, values.unsqueeze(0))
+
+    def store_post_at(self, t_dev: torch.Tensor, rewards, dones):
+        self.rewards.index_copy_(0, t_dev, rewards.unsqueeze(0))
+        self.dones.index_copy_(0, t_dev, dones.unsqueeze(0))
+
     def minibatch_obs(self, idx: torch.Tensor, sim, obs_dtype: Optional[str] = None):
         """Observations of flat sample indices `idx` (m = t*N + n)."""
         if self.store == "packed":
@@ -189,9 +202,14 @@ class PPOAgent:
             grid = torch.as_tensor(grid_tensors).to(self.device)
             extra = torch.as_tensor(extra_vectors).to(self.device)
             logits, values = self._forward(grid, extra, train=False)
-            dist = torch.distributions.Categorical(logits=logits)
-            actions = dist.sample()
-            log_probs = dist.log_prob(actions)
+            if as_numpy:  # the reference's exact sampling ops (ppo_agent.py:94-97)
+                dist = torch.distributions.Categorical(logits=logits)
+                actions = dist.sample()
+                log_probs = dist.log_prob(actions)
+            else:  # same distribution without Categorical's argument validation (a host sync):
+                logp = F.log_softmax(logits, dim=-1)  # capturable in a CUDA graph
+                actions = torch.multinomial(logp.exp(), 1).squeeze(1)
+                log_probs = logp.gather(1, actions.unsqueeze(1)).squeeze(1)
             values = values.squeeze(-1)
         if as_numpy:
             return actions.cpu().numpy(), log_probs.cpu().numpy(), values.cpu().numpy()

@@ -70,7 +70,7 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
           opponent_difficulty: str = "easy", load_model: Optional[str] = None, *, precision: str = "bf16",
           rollout_steps: Optional[int] = None, batch_size: Optional[int] = None, epochs: int = 4, lr: float = 1e-4,
           reference_gae: bool = False, seed: Optional[int] = None, max_episode_steps: int = 500,
-          save: bool = True, quiet: bool = False) -> dict:
+          save: bool = True, quiet: bool = False, cuda_graph: Optional[bool] = None) -> dict:
     """Shared body of train_vs_dummy / train_selfplay. `num_envs` is the GLOBAL env count; under
     torchrun each rank simulates its shard. Returns a summary dict (steps, episodes, win_rate,
     samples_per_s, ...)."""
@@ -85,6 +85,9 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
 
     if seed is not None:
         torch.manual_seed(seed + rank)
+    if precision == "fp32":  # the parity path: real fp32 convolutions, not TF32
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
     selfplay = mode == "selfplay"
     sim = BatchedInversus(n_local, "selfplay" if selfplay else "dummy", opponent_difficulty, max_episode_steps,
                           seed=seed, device=dev.index, obs_dtype="bf16" if precision == "bf16" else "f32",
@@ -126,16 +129,62 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
     iters = []      # (samples, rollout seconds, update seconds) per iteration
     iter_steps = 0
 
+    # Small batches are launch-bound (~60 kernels per env step: policy inference, sampling, the
+    # fused step, rollout stores). There the whole step is captured ONCE in a CUDA graph and
+    # replayed; the time index of the rollout lives on the device so the graph is step-invariant.
+    if cuda_graph is None:
+        cuda_graph = n_local <= 8192
+    exact_recent = exact_recent and not cuda_graph
+    t_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    step_graph = None
+
     def opponent_actions():
         # P2's view of the pre-step state (env_wrappers.py:311) is what the last step/reset emitted
         with torch.no_grad():
             logits, _ = (target_policy.infer(sim.obs_p2, sim.extra_p2) if precision == "bf16"
                          else target_policy(sim.obs_p2, sim.extra_p2))
-            return torch.distributions.Categorical(logits=logits).sample().to(torch.int8)
+            # Categorical(logits).sample() without its argument validation (a host sync that a CUDA
+            # graph cannot capture); training.py:255-257
+            return torch.multinomial(torch.softmax(logits, dim=-1), 1).squeeze(1).to(torch.int8)
+
+    def graphed_step():
+        actions, log_probs, values = agent.act(obs, extra)
+        rollout.store_pre_at(t_dev, sim, actions, log_probs, values)
+        a2 = opponent_actions() if selfplay else None
+        sim.step(actions.to(torch.int8), a2)
+        rollout.store_post_at(t_dev, sim.reward, sim.done)
+        d = sim.done.bool()
+        acc.add_(torch.stack([d.sum(), ((sim.info & INFO_WIN) != 0).sum(),
+                              torch.where(d, sim.episode_return, 0.0).sum(),
+                              torch.where(d, sim.episode_steps, 0).sum()]).to(torch.float64))
+        t_dev.add_(1)
+
+    if cuda_graph:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                t_dev.zero_()
+                graphed_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        step_graph = torch.cuda.CUDAGraph()
+        t_dev.zero_()
+        with torch.cuda.graph(step_graph):
+            graphed_step()
+        obs, extra = sim.reset()  # warm-up and capture stepped the envs: start fresh episodes
+        acc.zero_()
 
     while step_count < total_steps:
         t0 = time.time()
-        for _ in range(steps_per_env):
+        if cuda_graph:
+            t_dev.zero_()
+            n_steps = min(steps_per_env, -(-(total_steps - step_count) // num_envs))
+            for _ in range(n_steps):
+                step_graph.replay()
+            rollout.t = n_steps
+            step_count += n_steps * num_envs
+            rollout_env_steps += n_steps * num_envs
+        for _ in range(0 if cuda_graph else steps_per_env):
             actions, log_probs, values = agent.act(obs, extra)
             rollout.store_pre(sim, actions, log_probs, values)
             a2 = opponent_actions() if selfplay else None
@@ -163,6 +212,8 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
         if not reference_gae:
             last_value = agent.act(obs, extra)[2]
         update_stats = agent.update(rollout, sim, last_value)
+        if precision == "bf16":
+            policy.inference_weights()  # refresh the cached bf16 copies in place (the step graph reads them)
         torch.cuda.synchronize(dev)
         t2 = time.time()
         rollout_time += t1 - t0
@@ -172,6 +223,8 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
 
         if selfplay and step_count - last_opponent_update >= OPPONENT_UPDATE_FREQ:  # training.py:331-334
             target_policy.load_state_dict(policy.state_dict())
+            if precision == "bf16":
+                target_policy.inference_weights()
             last_opponent_update = step_count
 
         if step_count - last_log_step >= 1000 or step_count >= total_steps:  # training.py:172
@@ -211,7 +264,7 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
                "last_window": window,
                "wins_per_kstep": 1e3 * window["wins"] / max(window["steps"], 1),
                "n_gpus": world, "num_envs": num_envs, "steps_per_env": steps_per_env, "batch_size": batch_size,
-               "precision": precision}
+               "precision": precision, "cuda_graph": bool(cuda_graph)}
     sim.close()
     return summary
 
@@ -250,11 +303,14 @@ def main(argv=None):
     ap.add_argument("--batch_size", type=int, default=None)
     ap.add_argument("--reference-gae", action="store_true", help="flat-list GAE exactly like ppo_agent.py:127-157")
     ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--cuda-graph", choices=["auto", "on", "off"], default="auto",
+                    help="capture one rollout step in a CUDA graph (auto: when <= 8192 envs per GPU)")
     a = ap.parse_args(argv)
     log_dir = a.log_dir or f"runs/inversus_{a.mode}_envs{a.num_envs}"
     out = train(a.mode, a.num_envs, a.total_steps, log_dir, a.opponent_difficulty, a.load_model,
                 precision=a.precision, rollout_steps=a.rollout_steps, batch_size=a.batch_size,
-                reference_gae=a.reference_gae, seed=a.seed)
+                reference_gae=a.reference_gae, seed=a.seed,
+                cuda_graph={"auto": None, "on": True, "off": False}[a.cuda_graph])
     if dist_env()[0] == 0:
         print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in out.items()})
     if torch.distributed.is_initialized():

@@ -177,3 +177,54 @@ def test_fused_policy_path_matches_unfused():
     for (name, _), a, b in zip(m.named_parameters(), *grads):
         cs = torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0)
         assert cs > 0.99, (name, cs.item())
+
+
+def test_cuda_graph_rollout_fills_the_same_rollout_as_the_eager_loop(tmp_path):
+    """The graph-captured step (policy inference + sampling + fused env step + rollout stores, time
+    index on the device) must leave a complete, self-consistent rollout: with lr = 0 and fp32 the
+    stored values/log-probs must equal a fresh forward of the stored observations."""
+    import torch
+    from inversus_b200 import BatchedInversus, DeviceRollout, InversusCNNPolicy, PPOAgent
+    torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False  # true fp32 convolutions, so batch size does not change results
+    n, T = 64, 24
+    sim = BatchedInversus(n, "dummy", "hard", 30, seed=3, auto_reset=True)
+    agent = PPOAgent(InversusCNNPolicy(), device="cuda", precision="fp32")
+    ro = DeviceRollout(T, n, "cuda", store="packed")
+    obs, extra = sim.reset()
+    t_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def step():
+        a, lp, v = agent.act(obs, extra)
+        ro.store_pre_at(t_dev, sim, a, lp, v)
+        sim.step(a.to(torch.int8))
+        ro.store_post_at(t_dev, sim.reward, sim.done)
+        t_dev.add_(1)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            t_dev.zero_()
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    t_dev.zero_()
+    with torch.cuda.graph(graph):
+        step()
+    sim.reset()
+    t_dev.zero_()
+    for _ in range(T):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert int(t_dev.item()) == T
+    ro.t = T
+    idx = torch.arange(T * n, device="cuda")
+    g, e = ro.minibatch_obs(idx, sim)
+    with torch.no_grad():
+        logits, values = agent.policy(g, e)
+    lp = torch.log_softmax(logits, -1).gather(1, ro.actions.reshape(-1, 1)).squeeze(1)
+    assert torch.allclose(values.squeeze(-1), ro.values.reshape(-1), atol=1e-4)
+    assert torch.allclose(lp, ro.log_probs.reshape(-1), atol=1e-4)
+    assert int(ro.dones.sum()) > 0 and bool(torch.isfinite(ro.rewards).all())
+    assert sim.poll_status() == 0
