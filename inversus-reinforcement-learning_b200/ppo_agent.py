@@ -156,6 +156,7 @@ class PPOAgent:
         self.entropy_coef, self.value_coef = entropy_coef, value_coef
         self.gae_mode, self.precision, self.shuffle, self.generator = gae_mode, precision, shuffle, generator
         self.max_grad_norm = 0.5  # ppo_agent.py:228
+        self.act_chunk = 65536    # samples per inference micro-batch in act()
         self.reset_buffers()
 
     # ------------------------------------------------------------------ reference-shaped list buffers
@@ -201,7 +202,14 @@ class PPOAgent:
         with torch.no_grad():
             grid = torch.as_tensor(grid_tensors).to(self.device)
             extra = torch.as_tensor(extra_vectors).to(self.device)
-            logits, values = self._forward(grid, extra, train=False)
+            n = grid.shape[0]
+            if n > self.act_chunk:  # bound activation memory: 1M envs x 19200 features would be 38 GB per layer
+                parts = [self._forward(grid[i:i + self.act_chunk], extra[i:i + self.act_chunk], train=False)
+                         for i in range(0, n, self.act_chunk)]
+                logits = torch.cat([p[0] for p in parts])
+                values = torch.cat([p[1] for p in parts])
+            else:
+                logits, values = self._forward(grid, extra, train=False)
             if as_numpy:  # the reference's exact sampling ops (ppo_agent.py:94-97)
                 dist = torch.distributions.Categorical(logits=logits)
                 actions = dist.sample()

@@ -141,8 +141,12 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
     def opponent_actions():
         # P2's view of the pre-step state (env_wrappers.py:311) is what the last step/reset emitted
         with torch.no_grad():
-            logits, _ = (target_policy.infer(sim.obs_p2, sim.extra_p2) if precision == "bf16"
-                         else target_policy(sim.obs_p2, sim.extra_p2))
+            fwd = target_policy.infer if precision == "bf16" else target_policy
+            if n_local > agent.act_chunk:
+                logits = torch.cat([fwd(sim.obs_p2[i:i + agent.act_chunk], sim.extra_p2[i:i + agent.act_chunk])[0]
+                                    for i in range(0, n_local, agent.act_chunk)])
+            else:
+                logits, _ = fwd(sim.obs_p2, sim.extra_p2)
             # Categorical(logits).sample() without its argument validation (a host sync that a CUDA
             # graph cannot capture); training.py:255-257
             return torch.multinomial(torch.softmax(logits, dim=-1), 1).squeeze(1).to(torch.int8)

@@ -29,7 +29,14 @@ def run(name, **kw):
 
 
 if __name__ == "__main__":
-    if "--multi" in sys.argv:
+    if "--config4" in sys.argv:  # BASELINE.json configs[4] literally: 8 x 1 048 576 envs
+        world = dist_env()[2]
+        n = (1 << 20) * world
+        run(f"config4_vs_dummy_hard_{world}gpu_{n}envs", mode="vs_dummy", num_envs=n, total_steps=n * 8 * 2,
+            opponent_difficulty="hard", rollout_steps=8, batch_size=32768, epochs=1, precision="bf16")
+        if torch.distributed.is_initialized():
+            torch.distributed.destroy_process_group()
+    elif "--multi" in sys.argv:
         world = dist_env()[2]
         n = 131072 * world
         run(f"vs_dummy_hard_{world}gpu_sharded", mode="vs_dummy", num_envs=n, total_steps=n * 16 * 4,
