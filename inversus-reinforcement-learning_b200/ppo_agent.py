@@ -150,7 +150,8 @@ class PPOAgent:
         assert gae_mode in ("per_env", "reference") and precision in ("fp32", "bf16") and shuffle in ("torch", "numpy")
         self.device = torch.device(device)
         self.policy = policy.to(self.device)
-        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=lr)
+        # same Adam as the reference (ppo_agent.py:48); on CUDA the single-kernel fused implementation
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=lr, fused=self.device.type == "cuda")
         self.gamma, self.lam, self.clip_ratio = gamma, lam, clip_ratio
         self.epochs, self.batch_size = epochs, batch_size
         self.entropy_coef, self.value_coef = entropy_coef, value_coef
