@@ -41,6 +41,7 @@ class InversusCNNPolicy(nn.Module):
         self.flatten = nn.Flatten()
         self.feature_dim = _CONV_WIDTHS[-1] * height * width
         self.use_fused_kernels = True  # CUDA only: fused LayerNorm(+residual)+ReLU kernels in forward_bf16
+        self._weights_epoch = 0        # bumped by mark_updated(); part of the inference-cache key
         self.fc_actor = _mlp_head(self.feature_dim + extra_dim, hidden_dim, NUM_ACTIONS)
         self.fc_critic = _mlp_head(self.feature_dim + extra_dim, hidden_dim, 1)
 
@@ -136,12 +137,18 @@ class InversusCNNPolicy(nn.Module):
         and rebuilt only when a parameter changed (optimizer steps bump tensor versions)."""
         return self._forward_prepared(self.inference_weights(), grid_tensor, extra_vector)
 
+    def mark_updated(self) -> None:
+        """Tell the inference cache that the parameters changed (call after optimizer steps)."""
+        self._weights_epoch += 1
+
     @torch.no_grad()
     def inference_weights(self) -> dict:
         """The cached bf16 working copies used by `infer`. When a parameter changed they are
         refreshed IN PLACE (same tensors, same addresses), so a CUDA graph that captured `infer`
         keeps seeing current weights after an optimizer step."""
-        key = tuple(p._version for p in self.parameters()) + (str(self.conv1.weight.device),)
+        # tensor versions catch load_state_dict and ordinary in-place updates; fused optimizers
+        # (torch._fused_adam_) do NOT bump them, so trainers also call mark_updated()
+        key = tuple(p._version for p in self.parameters()) + (self._weights_epoch, str(self.conv1.weight.device))
         cache = getattr(self, "_infer_cache", None)
         if cache is None or cache[0][-1] != key[-1]:
             cache = [key, self._prepare_bf16()]

@@ -277,6 +277,8 @@ class PPOAgent:
                 self.optimizer.step()
                 sums += torch.stack([policy_loss.detach(), value_loss.detach(), entropy.detach()])
                 num_updates += 1
+        if hasattr(self.policy, "mark_updated"):
+            self.policy.mark_updated()  # fused optimizers do not bump tensor versions
         p, v, e = (sums / max(num_updates, 1)).tolist()  # the only host sync of the update
         return {"policy_loss": p, "value_loss": v, "entropy": e}
 

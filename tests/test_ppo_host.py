@@ -153,3 +153,17 @@ def test_inference_cache_follows_optimizer_steps():
     b = m.infer(g, e)
     assert not torch.equal(a[0], b[0])
     assert torch.equal(b[0], m.forward_bf16(g, e)[0].detach())
+    # fused optimizers do not bump tensor versions: the agent marks the policy updated itself, and the
+    # cached tensors are refreshed IN PLACE (a captured CUDA graph keeps reading the same addresses)
+    from inversus_b200.ppo_agent import PPOAgent
+    agent = PPOAgent(m, lr=0.05, epochs=1, batch_size=3)
+    agent.optimizer = torch.optim.Adam(m.parameters(), lr=0.05, fused=True)
+    cached = m.inference_weights()
+    ptrs = {k: v.data_ptr() for k, v in cached.items()}
+    for i in range(3):
+        agent.store_step(g[i].numpy(), e[i].numpy(), 1, -2.0, 0.0, 1.0, False)
+    agent.update()
+    c = m.infer(g, e)
+    assert not torch.equal(b[0], c[0])
+    assert torch.equal(c[0], m.forward_bf16(g, e)[0].detach())
+    assert {k: v.data_ptr() for k, v in m.inference_weights().items()} == ptrs
