@@ -173,6 +173,11 @@ int inv_set_host_path(inv_sim *sim, int nthreads, double dma_fraction);
 int inv_get_host_path(const inv_sim *sim, int *nthreads, double *dma_fraction, double *last_dma_s,
                       double *last_expand_s);
 
+/* The host half of that path, usable on its own (no GPU involved): expand packed observation rows
+ * bits[n][64] (u32; bit i of a row = observation element i, 1800 used) into dst[n][1800] f32 for
+ * rows [first, first+count), on nthreads host threads (AVX-512 / AVX2 non-temporal stores). */
+int inv_host_expand_f32(const uint32_t *bits, float *dst, int64_t first, int64_t count, int nthreads);
+
 /* page-locked host memory for the *_host calls (pageable memory works too, slower) */
 int inv_host_alloc(void **out, int64_t nbytes);
 int inv_host_free(void *p);

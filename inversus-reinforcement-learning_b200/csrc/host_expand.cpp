@@ -9,6 +9,7 @@
 // Pure format conversion: no game logic runs on the CPU.
 #include <immintrin.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <thread>
@@ -50,14 +51,50 @@ __attribute__((target("avx2"))) static void expand_avx2(const uint32_t *bits, fl
     _mm_sfence();
 }
 
+// AVX-512: envs are handled in pairs. One env is 1800 floats = 112.5 cache lines, so only every
+// second env starts on a 64-byte boundary; a pair is exactly 225 lines and every store is a full
+// non-temporal cache line. Line g of a pair holds elements [16g, 16g+16) of the concatenated
+// 3600-bit stream: lines 0..111 come from the first row, line 112 straddles the two rows, lines
+// 113..224 from the second row at a byte-shifted offset.
+__attribute__((target("avx512f,avx512bw,avx512vl"))) static void expand_avx512(const uint32_t *bits, float *dst,
+                                                                                int64_t lo, int64_t hi)
+{
+    const __m512 one = _mm512_set1_ps(1.0f);
+    int64_t e = lo;
+    if ((e & 1) && e < hi) { expand_avx2(bits, dst, e, e + 1); ++e; }              // odd head
+    for (; e + 1 < hi; e += 2) {
+        const uint8_t *r0 = reinterpret_cast<const uint8_t *>(bits + e * 64);
+        const uint8_t *r1 = reinterpret_cast<const uint8_t *>(bits + (e + 1) * 64);
+        float *o = dst + e * 1800;
+        for (int g = 0; g < 112; ++g) {
+            uint16_t m;
+            __builtin_memcpy(&m, r0 + 2 * g, 2);
+            _mm512_stream_ps(o + 16 * g, _mm512_maskz_mov_ps((__mmask16)m, one));
+        }
+        _mm512_stream_ps(o + 16 * 112, _mm512_maskz_mov_ps((__mmask16)(r0[224] | (r1[0] << 8)), one));
+        for (int g = 113; g < 225; ++g) {
+            uint16_t m;
+            __builtin_memcpy(&m, r1 + 2 * (g - 113) + 1, 2);
+            _mm512_stream_ps(o + 16 * g, _mm512_maskz_mov_ps((__mmask16)m, one));
+        }
+    }
+    if (e < hi) expand_avx2(bits, dst, e, hi);                                      // odd tail
+    _mm_sfence();
+}
+
 // Expand envs [lo, hi) of `bits` ([n][64] u32, little-endian bit i = observation element i) into
 // `dst` ([n][1800] f32) using up to `nthreads` threads.
 void expand_f32(const uint32_t *bits, float *dst, int64_t lo, int64_t hi, int nthreads)
 {
     if (hi <= lo) return;
     static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    static const bool have_avx512 = have_avx2 && __builtin_cpu_supports("avx512f") &&
+                                    __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") &&
+                                    !getenv("INV_NO_AVX512");
+    const bool aligned64 = (reinterpret_cast<uintptr_t>(dst) & 63u) == 0;
     auto work = [&](int64_t a, int64_t b) {
-        if (have_avx2) expand_avx2(bits, dst, a, b);
+        if (have_avx512 && aligned64) expand_avx512(bits, dst, a, b);
+        else if (have_avx2) expand_avx2(bits, dst, a, b);
         else expand_scalar(bits, dst, a, b);
     };
     const int64_t n = hi - lo;
@@ -65,7 +102,12 @@ void expand_f32(const uint32_t *bits, float *dst, int64_t lo, int64_t hi, int nt
     if (nt == 1) { work(lo, hi); return; }
     std::vector<std::thread> th;
     th.reserve(nt);
-    for (int t = 0; t < nt; ++t) th.emplace_back(work, lo + n * t / nt, lo + n * (t + 1) / nt);
+    auto cut = [&](int t) { // even boundaries keep the AVX-512 pairs aligned
+        if (t == 0) return lo;
+        if (t == nt) return hi;
+        return (lo + n * t / nt) & ~(int64_t)1;
+    };
+    for (int t = 0; t < nt; ++t) th.emplace_back(work, cut(t), cut(t + 1));
     for (auto &x : th) x.join();
 }
 
@@ -76,3 +118,12 @@ int hardware_threads()
 }
 
 } // namespace inv_host
+
+// C ABI (include/inversus_b200.h): host-side expansion of packed observation rows, usable on its own.
+extern "C" int inv_host_expand_f32(const uint32_t *bits, float *dst, int64_t first, int64_t count, int nthreads)
+{
+    if (!bits || !dst || first < 0 || count < 0) return -1;
+    inv_host::expand_f32(bits, dst, first, first + count, nthreads > 0 ? nthreads : 1);
+    return 0;
+}
+

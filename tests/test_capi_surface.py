@@ -84,3 +84,39 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("the oracle and the live-reference harness", ""), f
+
+
+@pytest.mark.parametrize("no_avx512", [False, True])
+def test_host_side_observation_expansion(no_avx512):
+    """inv_host_expand_f32 (the CPU half of inv_step_host's packed path) against numpy.unpackbits:
+    random rows, odd/even ranges, 1 and many threads, 64-byte-aligned and unaligned destinations.
+    Runs in a subprocess so that INV_NO_AVX512 can select the AVX2 path as well."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, sys, numpy as np
+sys.path.insert(0, %r)
+from inversus_b200 import _capi
+lib = _capi.load()
+rs = np.random.RandomState(0)
+n = 1031
+bits = rs.randint(0, 2**32, size=(n, 64), dtype=np.uint64).astype(np.uint32)
+want = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :1800].astype(np.float32)
+for off in (0, 8):                      # aligned / unaligned destination
+    raw = np.full(n * 1800 + 64, -7.0, np.float32)
+    base = (-raw.ctypes.data // 4) %% 16 + off
+    dst = raw[base: base + n * 1800].reshape(n, 1800)
+    for first, count, nt in ((0, n, 1), (0, n, 7), (1, n - 1, 3), (5, 600, 2), (6, 1, 1), (7, 0, 4)):
+        dst[:] = -7.0
+        rc = lib.inv_host_expand_f32(bits.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), first, count, nt)
+        assert rc == 0
+        assert np.array_equal(dst[first:first + count], want[first:first + count]), (off, first, count, nt)
+        assert (dst[:first] == -7.0).all() and (dst[first + count:] == -7.0).all()
+        assert raw[base - 1] == -7.0 and raw[base + n * 1800] == -7.0
+print("expand ok")
+''' % ROOT
+    env = dict(os.environ)
+    if no_avx512:
+        env["INV_NO_AVX512"] = "1"
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "expand ok" in r.stdout, r.stdout + r.stderr
