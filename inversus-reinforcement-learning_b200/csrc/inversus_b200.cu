@@ -154,11 +154,13 @@ cudaError_t launch_one(const Params &p, int sm_count, cudaStream_t st)
     (void)sm_count;
     auto kern = inv_kernel<OP, DT, P2V, INDEXED, E, T>;
     constexpr size_t smem = smem_bytes<E, P2V, INDEXED>();
-    static bool configured = false; // per instantiation
-    if (!configured) {
+    static bool configured[64] = {}; // per instantiation and per device (function attributes are per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     const int64_t ntiles = (p.count + E - 1) / E;
     if (ntiles <= 0) return cudaSuccess;

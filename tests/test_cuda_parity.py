@@ -245,3 +245,20 @@ def test_state_import_export_roundtrip_and_validation():
     x["tiles"][0][4] = 1 << 22  # bit beyond the 150 tiles
     with pytest.raises(ValueError):
         s.import_state(x)
+
+
+def test_two_devices_in_one_process():
+    """Handles on different GPUs of one process (function attributes and SM counts are per device)."""
+    import torch
+    from inversus_b200 import BatchedInversus
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sims = [BatchedInversus(5000, "selfplay", "hard", 50, seed=1, device=d, obs_dtype="u8") for d in (0, 1)]
+    rs = np.random.RandomState(0)
+    for s in sims:
+        s.reset()
+    for _ in range(5):
+        a1, a2 = rs.randint(0, 13, 5000).astype(np.int8), rs.randint(0, 13, 5000).astype(np.int8)
+        for d, s in enumerate(sims):
+            s.step(torch.from_numpy(a1).cuda(d), torch.from_numpy(a2).cuda(d))
+    assert torch.equal(sims[0].obs.cpu(), sims[1].obs.cpu()) and torch.equal(sims[0].reward.cpu(), sims[1].reward.cpu())
