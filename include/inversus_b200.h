@@ -225,6 +225,12 @@ int inv_gae(const float *reward_dev, const float *value_dev, const uint8_t *done
  *        inv_ln_relu_partials(D) * 2 * D floats. All pointers are device pointers on the current
  *        device. */
 int inv_ln_relu_partials(int32_t D);
+/* Per-row transpose + fp32<->bf16 conversion: dst[r][b*A + a] = src[r][a*B + b], a < A, b < B, for
+ * `rows` rows with leading dimensions ld_src / ld_dst (elements). Exactly one side is fp32, the
+ * other bf16. Carries the head weight of policies.py:61-75 between the checkpoint's CHW column
+ * order and the HWC order of channels-last activations (and the gradient back). */
+int inv_transpose_cast(const void *src, int32_t src_is_f32, int64_t ld_src, void *dst, int32_t dst_is_f32,
+                       int64_t ld_dst, int64_t rows, int32_t A, int32_t B, void *stream);
 int inv_ln_relu_fwd(const void *x, const void *res, const void *gamma, const void *beta, int64_t B, int32_t D,
                     float eps, void *y, float *mean, float *rstd, void *stream);
 int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *gamma, const void *beta,

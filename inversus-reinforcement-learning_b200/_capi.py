@@ -74,6 +74,8 @@ SYMBOLS = {
     "inv_ln_relu_partials": (C.c_int, [C.c_int32]),
     "inv_ln_relu_fwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float] + [C.c_void_p] * 4),
     "inv_ln_relu_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_int32] + [C.c_void_p] * 5),
+    "inv_transpose_cast": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
+                                     C.c_int32, C.c_int32, C.c_void_p]),
     "inv_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32,
                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

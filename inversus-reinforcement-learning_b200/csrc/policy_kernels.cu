@@ -262,6 +262,30 @@ __global__ void reduce_partials_kernel(const float *__restrict__ partials, int n
     else dbeta[i - D] = s;
 }
 
+// Per-row transpose with dtype conversion: dst[r][b*A + a] = src[r][a*B + b] for a < A, b < B.
+// Used to bring the 19200 trunk columns of the fused head weight from the checkpoint's CHW order
+// (fp32 master) to the HWC order of the channels-last activations (bf16 working copy), and to
+// carry the gradient back. 32x32 shared-memory tiles, coalesced on both sides.
+template <typename TS, typename TD>
+__global__ void transpose_cast_kernel(const TS *__restrict__ src, int64_t ld_src, TD *__restrict__ dst,
+                                      int64_t ld_dst, int A, int B)
+{
+    __shared__ float tile[32][33];
+    const int64_t r = blockIdx.z;
+    const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+    const TS *s = src + r * ld_src;
+    TD *d = dst + r * ld_dst;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int a = a0 + i, b = b0 + threadIdx.x;
+        if (a < A && b < B) tile[i][threadIdx.x] = (float)s[(int64_t)a * B + b];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int b = b0 + i, a = a0 + threadIdx.x;
+        if (a < A && b < B) d[(int64_t)b * A + a] = (TD)tile[threadIdx.x][i];
+    }
+}
+
 int sm_count_cached()
 {
     static int n[64] = {};
@@ -278,6 +302,23 @@ int sm_count_cached()
 } // namespace
 
 extern "C" {
+
+int inv_transpose_cast(const void *src, int32_t src_is_f32, int64_t ld_src, void *dst, int32_t dst_is_f32,
+                       int64_t ld_dst, int64_t rows, int32_t A, int32_t B, void *stream)
+{
+    if (!src || !dst || rows < 0 || A <= 0 || B <= 0 || rows > 65535 || src_is_f32 == dst_is_f32)
+        return INV_ERR_INVALID_ARG;
+    if (rows == 0) return INV_OK;
+    const dim3 grid((B + 31) / 32, (A + 31) / 32, (unsigned)rows), block(32, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_is_f32)
+        transpose_cast_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>(
+            (const float *)src, ld_src, (__nv_bfloat16 *)dst, ld_dst, A, B);
+    else
+        transpose_cast_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>(
+            (const __nv_bfloat16 *)src, ld_src, (float *)dst, ld_dst, A, B);
+    return cudaGetLastError() == cudaSuccess ? INV_OK : INV_ERR_CUDA;
+}
 
 int inv_ln_relu_partials(int32_t D) { (void)D; return sm_count_cached(); }
 

@@ -60,3 +60,33 @@ def layer_norm_relu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, ep
                     residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """relu(LayerNorm_over_dim1(x [+ residual]) * gamma + beta) for bf16 CUDA tensors [B, D]."""
     return _LNReLU.apply(x, residual, gamma, beta, eps)
+
+
+class _HeadWeightToHWC(torch.autograd.Function):
+    """fp32 [R, >= C*P] (columns in CHW order) -> bf16 [R, P*C] (HWC order); gradient back."""
+
+    @staticmethod
+    def forward(ctx, w, C_, P_):
+        assert w.is_cuda and w.dtype == torch.float32 and w.dim() == 2 and w.stride(1) == 1
+        R = w.shape[0]
+        out = torch.empty((R, C_ * P_), dtype=torch.bfloat16, device=w.device)
+        with torch.cuda.device(w.device):
+            _capi.check(_capi.load().inv_transpose_cast(w.data_ptr(), 1, w.stride(0), out.data_ptr(), 0, C_ * P_,
+                                                        R, C_, P_, _stream(w)))
+        ctx.shape, ctx.cp = w.shape, (C_, P_)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        C_, P_ = ctx.cp
+        g = g.contiguous()
+        gw = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)  # extra columns get no gradient here
+        with torch.cuda.device(g.device):
+            _capi.check(_capi.load().inv_transpose_cast(g.data_ptr(), 0, C_ * P_, gw.data_ptr(), 1, gw.stride(0),
+                                                        g.shape[0], P_, C_, _stream(g)))
+        return gw, None, None
+
+
+def head_weight_to_hwc(w: torch.Tensor, channels: int, positions: int) -> torch.Tensor:
+    """bf16 HWC-ordered copy of the first channels*positions columns of the fp32 head weight."""
+    return _HeadWeightToHWC.apply(w, channels, positions)

@@ -77,7 +77,11 @@ class InversusCNNPolicy(nn.Module):
         a0, c0 = self.fc_actor[0], self.fc_critic[0]
         w0 = torch.cat([a0.weight, c0.weight], 0)                # [2*hidden, 19200 + extra]
         c = nf // (H * W)
-        prep["w_feat"] = w0[:, :nf].to(bf).reshape(-1, c, H * W).permute(0, 2, 1).reshape(-1, nf)  # CHW -> HWC columns
+        if w0.is_cuda and self.use_fused_kernels:  # one tiled transpose+cast kernel each way (csrc/policy_kernels.cu)
+            from .fused_ops import head_weight_to_hwc
+            prep["w_feat"] = head_weight_to_hwc(w0, c, H * W)
+        else:
+            prep["w_feat"] = w0[:, :nf].to(bf).reshape(-1, c, H * W).permute(0, 2, 1).reshape(-1, nf)  # CHW -> HWC columns
         pad = (8 - self.extra_dim % 8) % 8
         prep["w_extra"] = F.pad(w0[:, nf:], (0, pad)).to(bf)
         prep["b0"] = torch.cat([a0.bias, c0.bias], 0).to(bf)

@@ -228,3 +228,19 @@ def test_cuda_graph_rollout_fills_the_same_rollout_as_the_eager_loop(tmp_path):
     assert torch.allclose(lp, ro.log_probs.reshape(-1), atol=1e-4)
     assert int(ro.dones.sum()) > 0 and bool(torch.isfinite(ro.rewards).all())
     assert sim.poll_status() == 0
+
+
+def test_head_weight_transpose_cast_kernel():
+    import torch
+    from inversus_b200.fused_ops import head_weight_to_hwc
+    torch.manual_seed(0)
+    for R, C_, P_, extra in ((512, 128, 150, 4), (3, 5, 7, 0), (40, 33, 65, 9)):
+        w = torch.randn(R, C_ * P_ + extra, device="cuda", requires_grad=True)
+        out = head_weight_to_hwc(w, C_, P_)
+        want = w[:, : C_ * P_].detach().to(torch.bfloat16).reshape(R, C_, P_).permute(0, 2, 1).reshape(R, -1)
+        assert torch.equal(out, want)
+        g = torch.randn_like(out)
+        out.backward(g)
+        gw = torch.zeros_like(w)
+        gw[:, : C_ * P_] = g.float().reshape(R, P_, C_).permute(0, 2, 1).reshape(R, -1)
+        assert torch.equal(w.grad, gw)
