@@ -216,26 +216,29 @@ int inv_gae(const float *reward_dev, const float *value_dev, const uint8_t *done
             const float *last_value_dev, double gamma, double lam, int32_t T, int64_t N, float *adv_dev,
             float *ret_dev, void *stream);
 
-/* Fused LayerNorm(+residual)+ReLU of the policy's channels-last bf16 path (the memory-bound glue
- * between the convolutions of inversus_rl/policies.py:27-45,94-100; the contractions themselves stay
- * in cuDNN/cuBLAS). A sample is D = H*W*C contiguous bf16 values in HWC order, gamma/beta are [D]
- * bf16 in the same order, statistics are fp32. res may be NULL. D % 8 == 0, D <= 20480.
- *   fwd: y = relu(LN(x [+ res]) * gamma + beta); writes mean[B], rstd[B] for the backward.
- *   bwd: dx (also the gradient of res), dgamma[D], dbeta[D] (fp32); partials is scratch of
- *        inv_ln_relu_partials(D) * 2 * D floats. All pointers are device pointers on the current
- *        device. */
+/* Fused (conv bias +) (residual +) LayerNorm + ReLU of the policy's channels-last bf16 path (the
+ * memory-bound glue between the convolutions of inversus_rl/policies.py:27-45,94-100; the
+ * contractions themselves stay in cuDNN/cuBLAS, run bias-free). A sample is D = H*W*C contiguous
+ * bf16 values in HWC order, gamma/beta are [D] bf16 in the same order, cbias is the [C] bf16
+ * per-channel convolution bias (may be NULL), statistics are fp32. res may be NULL.
+ * D % C == 0, C % 8 == 0, 512 % (C/8) == 0, D <= 20480.
+ *   fwd: y = relu(LN(x + cbias [+ res]) * gamma + beta); writes mean[B], rstd[B] for the backward.
+ *   bwd: dx (also the gradient of res), dgamma[D], dbeta[D], dcbias[C] (fp32, dcbias may be NULL);
+ *        partials is scratch of inv_ln_relu_partials(D) * (2*D + C) floats.
+ * All pointers are device pointers on the current device. */
 int inv_ln_relu_partials(int32_t D);
+int inv_ln_relu_fwd(const void *x, const void *res, const void *cbias, const void *gamma, const void *beta,
+                    int64_t B, int32_t D, int32_t C, float eps, void *y, float *mean, float *rstd, void *stream);
+int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *cbias, const void *gamma,
+                    const void *beta, const float *mean, const float *rstd, int64_t B, int32_t D, int32_t C,
+                    void *dx, float *dgamma, float *dbeta, float *dcbias, float *partials, void *stream);
+
 /* Per-row transpose + fp32<->bf16 conversion: dst[r][b*A + a] = src[r][a*B + b], a < A, b < B, for
  * `rows` rows with leading dimensions ld_src / ld_dst (elements). Exactly one side is fp32, the
  * other bf16. Carries the head weight of policies.py:61-75 between the checkpoint's CHW column
  * order and the HWC order of channels-last activations (and the gradient back). */
 int inv_transpose_cast(const void *src, int32_t src_is_f32, int64_t ld_src, void *dst, int32_t dst_is_f32,
                        int64_t ld_dst, int64_t rows, int32_t A, int32_t B, void *stream);
-int inv_ln_relu_fwd(const void *x, const void *res, const void *gamma, const void *beta, int64_t B, int32_t D,
-                    float eps, void *y, float *mean, float *rstd, void *stream);
-int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *gamma, const void *beta,
-                    const float *mean, const float *rstd, int64_t B, int32_t D, void *dx, float *dgamma,
-                    float *dbeta, float *partials, void *stream);
 
 /* kernel launches issued through this handle so far (bench.py's gpu_launches) */
 int64_t inv_launch_count(const inv_sim *sim);

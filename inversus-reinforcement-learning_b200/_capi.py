@@ -72,8 +72,8 @@ SYMBOLS = {
     "inv_poll_status": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_uint32)]),
     "inv_launch_count": (C.c_int64, [C.c_void_p]),
     "inv_ln_relu_partials": (C.c_int, [C.c_int32]),
-    "inv_ln_relu_fwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float] + [C.c_void_p] * 4),
-    "inv_ln_relu_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_int32] + [C.c_void_p] * 5),
+    "inv_ln_relu_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_int32, C.c_float] + [C.c_void_p] * 4),
+    "inv_ln_relu_bwd": (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 6),
     "inv_transpose_cast": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
                                      C.c_int32, C.c_int32, C.c_void_p]),
     "inv_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32,

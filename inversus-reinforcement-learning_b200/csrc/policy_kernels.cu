@@ -64,17 +64,21 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2 *scratch)
 }
 
 // Two CTAs per SM (<= 64 registers at 512 threads): while one CTA sits in its block reduction the
-// other streams. gamma/beta are cached in registers only for the narrow layers (MAXV <= 2); the
-// wide ones re-read them per sample from L1/L2.
+// other streams. gamma/beta are re-read per sample from L1/L2 (caching them in registers would not
+// fit the 64-register budget together with the packed inputs).
 template <int MAXV, bool HAS_RES>
 __global__ void __launch_bounds__(kLnThreads, 2)
-ln_relu_fwd_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ res, const uint4 *__restrict__ gamma,
-                   const uint4 *__restrict__ beta, int64_t B, int nvec, float eps, uint4 *__restrict__ y,
-                   float *__restrict__ mean_out, float *__restrict__ rstd_out)
+ln_relu_fwd_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ res, const uint4 *__restrict__ cbias,
+                   int cvecs, const uint4 *__restrict__ gamma, const uint4 *__restrict__ beta, int64_t B, int nvec,
+                   float eps, uint4 *__restrict__ y, float *__restrict__ mean_out, float *__restrict__ rstd_out)
 {
     __shared__ float2 scratch[kLnThreads / 32];
     const int tid = threadIdx.x;
-    constexpr bool kCacheGB = MAXV <= 2;
+    // per-channel convolution bias, folded in here so cuDNN runs bias-free: the element (i*8 + j) of
+    // an HWC sample belongs to channel ((i mod C/8)*8 + j), and since kLnThreads is a multiple of
+    // C/8 every vector of a thread sees the same 8 channels -> one register vector per thread
+    const uint4 cbv = cbias ? cbias[tid % cvecs] : make_uint4(0u, 0u, 0u, 0u); // kept packed: 4 registers
+    constexpr bool kCacheGB = MAXV <= 1;
     uint4 g[kCacheGB ? MAXV : 1], bt[kCacheGB ? MAXV : 1];
     if (kCacheGB) {
 #pragma unroll
@@ -102,6 +106,12 @@ ln_relu_fwd_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ res, c
             if (i < nvec) {
                 float z[8];
                 unpack8(xv[k], z);
+                {
+                    float cb[8];
+                    unpack8(cbv, cb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] += cb[j];
+                }
                 if (HAS_RES) {
                     float r[8];
                     unpack8(rv[k], r);
@@ -123,6 +133,12 @@ ln_relu_fwd_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ res, c
             if (i < nvec) {
                 float z[8], gf[8], bf[8], o[8];
                 unpack8(xv[k], z);
+                {
+                    float cb[8];
+                    unpack8(cbv, cb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] += cb[j];
+                }
                 if (HAS_RES) {
                     float r[8];
                     unpack8(rv[k], r);
@@ -143,7 +159,8 @@ ln_relu_fwd_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ res, c
 template <int MAXV, bool HAS_RES>
 __global__ void __launch_bounds__(kLnThreads)
 ln_relu_bwd_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, const uint4 *__restrict__ res,
-                   const uint4 *__restrict__ gamma, const uint4 *__restrict__ beta, const float *__restrict__ mean_in,
+                   const uint4 *__restrict__ cbias, int cvecs, const uint4 *__restrict__ gamma,
+                   const uint4 *__restrict__ beta, const float *__restrict__ mean_in,
                    const float *__restrict__ rstd_in, int64_t B, int nvec, uint4 *__restrict__ dx,
                    float *__restrict__ partials)
 {
@@ -151,6 +168,9 @@ ln_relu_bwd_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, co
     __shared__ float2 scratch[kLnThreads / 32];
     const int tid = threadIdx.x;
     const int D = nvec * 8;
+    float cb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (cbias) unpack8(cbias[tid % cvecs], cb);
+    float db[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; // d(conv bias) of this thread's 8 channels
     for (int i = tid; i < 2 * D; i += kLnThreads) acc[i] = 0.f;
     __syncthreads();
     // gamma/beta live in registers across samples when the slice is small; for the two 19200-wide
@@ -187,6 +207,8 @@ ln_relu_bwd_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, co
             if (i < nvec) {
                 float z[8], d[8], gf[8], bf[8];
                 unpack8(xv[k], z);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) z[j] += cb[j];
                 if (HAS_RES) {
                     float r[8];
                     unpack8(rv[k], r);
@@ -219,6 +241,8 @@ ln_relu_bwd_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, co
             if (i < nvec) {
                 float z[8], d[8], gf[8], bf[8], o[8];
                 unpack8(xv[k], z);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) z[j] += cb[j];
                 if (HAS_RES) {
                     float r[8];
                     unpack8(rv[k], r);
@@ -233,12 +257,14 @@ ln_relu_bwd_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, co
                     const float h = (z[j] - mean) * rstd;
                     const float w = (h * gf[j] + bf[j] > 0.f) ? d[j] * gf[j] : 0.f;
                     o[j] = rstd * (w - m1 - h * m2);
+                    db[j] += o[j];
                 }
                 dx[s * nvec + i] = pack8(o);
             }
         }
     }
-    float *out = partials + (size_t)blockIdx.x * 2 * D;
+    const int C = cvecs * 8;
+    float *out = partials + (size_t)blockIdx.x * (2 * D + C);
     for (int k = 0; k < MAXV; ++k) {
         const int i = k * kLnThreads + tid;
         if (i < nvec) {
@@ -249,17 +275,31 @@ ln_relu_bwd_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, co
             }
         }
     }
+    // d(conv bias): every thread holds sums for channels (tid % cvecs)*8 .. +7; fold the
+    // kLnThreads / cvecs threads of each channel group through shared memory (acc is free now)
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[tid * 8 + j] = db[j];
+    __syncthreads();
+    if (tid < C) {
+        const int grp = tid >> 3, j = tid & 7;
+        float sum = 0.f;
+        for (int t = grp; t < kLnThreads; t += cvecs) sum += acc[t * 8 + j];
+        out[2 * D + tid] = sum;
+    }
 }
 
-__global__ void reduce_partials_kernel(const float *__restrict__ partials, int nparts, int n2d,
-                                       float *__restrict__ dgamma, float *__restrict__ dbeta, int D)
+__global__ void reduce_partials_kernel(const float *__restrict__ partials, int nparts, int width,
+                                       float *__restrict__ dgamma, float *__restrict__ dbeta,
+                                       float *__restrict__ dcbias, int D)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n2d) return;
+    if (i >= width) return;
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * n2d + i];
+    for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * width + i];
     if (i < D) dgamma[i] = s;
-    else dbeta[i - D] = s;
+    else if (i < 2 * D) dbeta[i - D] = s;
+    else if (dcbias) dcbias[i - 2 * D] = s;
 }
 
 // Per-row transpose with dtype conversion: dst[r][b*A + a] = src[r][a*B + b] for a < A, b < B.
@@ -322,10 +362,12 @@ int inv_transpose_cast(const void *src, int32_t src_is_f32, int64_t ld_src, void
 
 int inv_ln_relu_partials(int32_t D) { (void)D; return sm_count_cached(); }
 
-int inv_ln_relu_fwd(const void *x, const void *res, const void *gamma, const void *beta, int64_t B, int32_t D,
-                    float eps, void *y, float *mean, float *rstd, void *stream)
+int inv_ln_relu_fwd(const void *x, const void *res, const void *cbias, const void *gamma, const void *beta,
+                    int64_t B, int32_t D, int32_t C, float eps, void *y, float *mean, float *rstd, void *stream)
 {
     if (!x || !gamma || !beta || !y || !mean || !rstd || B < 0 || D <= 0 || D % 8) return INV_ERR_INVALID_ARG;
+    if (C <= 0 || C % 8 || D % C || kLnThreads % (C / 8)) return INV_ERR_INVALID_ARG;
+    const int cvecs = C / 8;
     if (B == 0) return INV_OK;
     const int nvec = D / 8;
     const int maxv = (nvec + kLnThreads - 1) / kLnThreads;
@@ -336,10 +378,12 @@ int inv_ln_relu_fwd(const void *x, const void *res, const void *gamma, const voi
 #define LAUNCH(MV)                                                                                              \
     if (res)                                                                                                    \
         ln_relu_fwd_kernel<MV, true><<<grid, kLnThreads, 0, st>>>((const uint4 *)x, (const uint4 *)res,         \
-            (const uint4 *)gamma, (const uint4 *)beta, B, nvec, eps, (uint4 *)y, mean, rstd);                    \
+            (const uint4 *)cbias, cvecs, (const uint4 *)gamma, (const uint4 *)beta, B, nvec, eps, (uint4 *)y,    \
+            mean, rstd);                                                                                        \
     else                                                                                                        \
         ln_relu_fwd_kernel<MV, false><<<grid, kLnThreads, 0, st>>>((const uint4 *)x, nullptr,                   \
-            (const uint4 *)gamma, (const uint4 *)beta, B, nvec, eps, (uint4 *)y, mean, rstd);
+            (const uint4 *)cbias, cvecs, (const uint4 *)gamma, (const uint4 *)beta, B, nvec, eps, (uint4 *)y,    \
+            mean, rstd);
     switch (maxv) {
     case 1: LAUNCH(1) break;
     case 2: LAUNCH(2) break;
@@ -351,30 +395,34 @@ int inv_ln_relu_fwd(const void *x, const void *res, const void *gamma, const voi
     return cudaGetLastError() == cudaSuccess ? INV_OK : INV_ERR_CUDA;
 }
 
-int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *gamma, const void *beta,
-                    const float *mean, const float *rstd, int64_t B, int32_t D, void *dx, float *dgamma,
-                    float *dbeta, float *partials, void *stream)
+int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *cbias, const void *gamma,
+                    const void *beta, const float *mean, const float *rstd, int64_t B, int32_t D, int32_t C,
+                    void *dx, float *dgamma, float *dbeta, float *dcbias, float *partials, void *stream)
 {
     if (!dy || !x || !gamma || !beta || !mean || !rstd || !dx || !dgamma || !dbeta || !partials || B <= 0 ||
         D <= 0 || D % 8)
         return INV_ERR_INVALID_ARG;
+    if (C <= 0 || C % 8 || D % C || kLnThreads % (C / 8) || C > kLnThreads) return INV_ERR_INVALID_ARG;
+    const int cvecs = C / 8;
     const int nvec = D / 8;
     const int maxv = (nvec + kLnThreads - 1) / kLnThreads;
     if (maxv > 5) return INV_ERR_INVALID_ARG;
     const int nsm = sm_count_cached();
     const unsigned grid = (unsigned)(B < nsm ? B : nsm); // one CTA per SM: 2*D floats of shared memory each
-    const size_t smem = (size_t)2 * D * sizeof(float);
+    size_t smem = (size_t)2 * D * sizeof(float);
+    if (smem < (size_t)kLnThreads * 8 * sizeof(float)) smem = (size_t)kLnThreads * 8 * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(MV)                                                                                              \
     if (res) {                                                                                                  \
         cudaFuncSetAttribute(ln_relu_bwd_kernel<MV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         ln_relu_bwd_kernel<MV, true><<<grid, kLnThreads, smem, st>>>((const uint4 *)dy, (const uint4 *)x,       \
-            (const uint4 *)res, (const uint4 *)gamma, (const uint4 *)beta, mean, rstd, B, nvec, (uint4 *)dx,     \
-            partials);                                                                                          \
+            (const uint4 *)res, (const uint4 *)cbias, cvecs, (const uint4 *)gamma, (const uint4 *)beta, mean,    \
+            rstd, B, nvec, (uint4 *)dx, partials);                                                              \
     } else {                                                                                                    \
         cudaFuncSetAttribute(ln_relu_bwd_kernel<MV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         ln_relu_bwd_kernel<MV, false><<<grid, kLnThreads, smem, st>>>((const uint4 *)dy, (const uint4 *)x,      \
-            nullptr, (const uint4 *)gamma, (const uint4 *)beta, mean, rstd, B, nvec, (uint4 *)dx, partials);     \
+            nullptr, (const uint4 *)cbias, cvecs, (const uint4 *)gamma, (const uint4 *)beta, mean, rstd, B,      \
+            nvec, (uint4 *)dx, partials);                                                                       \
     }
     switch (maxv) {
     case 1: LAUNCH(1) break;
@@ -385,8 +433,8 @@ int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *
     }
 #undef LAUNCH
     if (cudaGetLastError() != cudaSuccess) return INV_ERR_CUDA;
-    const int n2d = 2 * D;
-    reduce_partials_kernel<<<(n2d + 255) / 256, 256, 0, st>>>(partials, (int)grid, n2d, dgamma, dbeta, D);
+    const int width = 2 * D + C;
+    reduce_partials_kernel<<<(width + 255) / 256, 256, 0, st>>>(partials, (int)grid, width, dgamma, dbeta, dcbias, D);
     return cudaGetLastError() == cudaSuccess ? INV_OK : INV_ERR_CUDA;
 }
 

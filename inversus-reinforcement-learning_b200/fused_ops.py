@@ -20,46 +20,60 @@ def _stream(t: torch.Tensor) -> int:
 
 class _LNReLU(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, eps):
+    def forward(ctx, x, res, cbias, gamma, beta, eps, channels):
         assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous()
         B, D = x.shape
         assert gamma.dtype == torch.bfloat16 and gamma.numel() == D and beta.numel() == D
         gamma, beta = gamma.contiguous(), beta.contiguous()
         if res is not None:
             assert res.shape == x.shape and res.dtype == torch.bfloat16 and res.is_contiguous()
+        if cbias is not None:
+            assert cbias.dtype == torch.bfloat16 and cbias.numel() == channels
+            cbias = cbias.contiguous()
         y = torch.empty_like(x)
         mean = torch.empty(B, dtype=torch.float32, device=x.device)
         rstd = torch.empty(B, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             _capi.check(_capi.load().inv_ln_relu_fwd(
-                x.data_ptr(), None if res is None else res.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, D,
-                float(eps), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _stream(x)))
-        ctx.save_for_backward(x, res if res is not None else x.new_empty(0), gamma, beta, mean, rstd)
-        ctx.has_res = res is not None
+                x.data_ptr(), None if res is None else res.data_ptr(), None if cbias is None else cbias.data_ptr(),
+                gamma.data_ptr(), beta.data_ptr(), B, D, channels, float(eps), y.data_ptr(), mean.data_ptr(),
+                rstd.data_ptr(), _stream(x)))
+        empty = x.new_empty(0)
+        ctx.save_for_backward(x, res if res is not None else empty, cbias if cbias is not None else empty,
+                              gamma, beta, mean, rstd)
+        ctx.has_res, ctx.has_cb, ctx.channels = res is not None, cbias is not None, channels
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, res, gamma, beta, mean, rstd = ctx.saved_tensors
+        x, res, cbias, gamma, beta, mean, rstd = ctx.saved_tensors
         B, D = x.shape
+        C_ = ctx.channels
         dy = dy.contiguous()
         lib = _capi.load()
         dx = torch.empty_like(x)
         dgamma = torch.empty(D, dtype=torch.float32, device=x.device)
         dbeta = torch.empty(D, dtype=torch.float32, device=x.device)
+        dcb = torch.empty(C_, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            partials = torch.empty((lib.inv_ln_relu_partials(D), 2 * D), dtype=torch.float32, device=x.device)
+            partials = torch.empty((lib.inv_ln_relu_partials(D), 2 * D + C_), dtype=torch.float32, device=x.device)
             _capi.check(lib.inv_ln_relu_bwd(
-                dy.data_ptr(), x.data_ptr(), res.data_ptr() if ctx.has_res else None, gamma.data_ptr(),
-                beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(), B, D, dx.data_ptr(), dgamma.data_ptr(),
-                dbeta.data_ptr(), partials.data_ptr(), _stream(x)))
-        return dx, (dx if ctx.has_res else None), dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None
+                dy.data_ptr(), x.data_ptr(), res.data_ptr() if ctx.has_res else None,
+                cbias.data_ptr() if ctx.has_cb else None, gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
+                rstd.data_ptr(), B, D, C_, dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), dcb.data_ptr(),
+                partials.data_ptr(), _stream(x)))
+        return (dx, (dx if ctx.has_res else None), (dcb.to(cbias.dtype) if ctx.has_cb else None),
+                dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None, None)
 
 
 def layer_norm_relu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
-                    residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """relu(LayerNorm_over_dim1(x [+ residual]) * gamma + beta) for bf16 CUDA tensors [B, D]."""
-    return _LNReLU.apply(x, residual, gamma, beta, eps)
+                    residual: Optional[torch.Tensor] = None, channel_bias: Optional[torch.Tensor] = None,
+                    channels: Optional[int] = None) -> torch.Tensor:
+    """relu(LayerNorm_over_dim1(x + channel_bias [+ residual]) * gamma + beta) for bf16 CUDA tensors
+    [B, D] whose rows are HWC-ordered feature maps with `channels` channels (channel = index % channels)."""
+    if channels is None:
+        channels = channel_bias.numel() if channel_bias is not None else 8
+    return _LNReLU.apply(x, residual, channel_bias, gamma, beta, eps, channels)
 
 
 class _HeadWeightToHWC(torch.autograd.Function):

@@ -99,14 +99,16 @@ class InversusCNNPolicy(nn.Module):
         fused = x.is_cuda and self.use_fused_kernels
         res = None
         for i in (1, 2, 3, 4):
-            y = F.conv2d(x, prep[f"cw{i}"], prep[f"cb{i}"], padding=1)
+            # fused path: cuDNN runs bias-free, the per-channel bias is added inside the LayerNorm kernel
+            y = F.conv2d(x, prep[f"cw{i}"], None if fused else prep[f"cb{i}"], padding=1)
             eps = getattr(self, f"norm{i}").eps
             yp = y.permute(0, 2, 3, 1)                           # [B,H,W,C] view of channels-last memory
             c = yp.shape[-1]
-            if fused:  # one hand-written kernel: (+residual) -> LayerNorm -> affine -> ReLU (csrc/policy_kernels.cu)
+            if fused:  # one hand-written kernel: +bias (+residual) -> LayerNorm -> affine -> ReLU (csrc/policy_kernels.cu)
                 from .fused_ops import layer_norm_relu
                 flat = layer_norm_relu(yp.reshape(nb, -1), prep[f"nw{i}"].reshape(-1), prep[f"nb{i}"].reshape(-1), eps,
-                                       residual=res.permute(0, 2, 3, 1).reshape(nb, -1) if i == 4 else None)
+                                       residual=res.permute(0, 2, 3, 1).reshape(nb, -1) if i == 4 else None,
+                                       channel_bias=prep[f"cb{i}"], channels=c)
                 x = flat.view(nb, H, W, c).permute(0, 3, 1, 2)
             else:
                 if i == 4:

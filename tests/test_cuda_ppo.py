@@ -136,16 +136,20 @@ def test_fused_layernorm_relu_kernels_match_torch():
                 g = (torch.rand(D, device="cuda") + 0.5).to(torch.bfloat16).requires_grad_()
                 b = (torch.rand(D, device="cuda") - 0.5).to(torch.bfloat16).requires_grad_()
                 dy = torch.randn(B, D, device="cuda").to(torch.bfloat16)
-                y = layer_norm_relu(x, g, b, 1e-5, residual=r)
+                C_ = {4800: 32, 9600: 64, 19200: 128}[D]
+                cb = torch.randn(C_, device="cuda").to(torch.bfloat16).requires_grad_()  # folded conv bias
+                y = layer_norm_relu(x, g, b, 1e-5, residual=r, channel_bias=cb, channels=C_)
                 y.backward(dy)
                 xf = x.detach().float().requires_grad_()
                 rf = r.detach().float().requires_grad_() if with_res else None
                 gf, bf_ = g.detach().float().requires_grad_(), b.detach().float().requires_grad_()
-                z = xf + rf if with_res else xf
+                cbf = cb.detach().float().requires_grad_()
+                z = xf + cbf.repeat(D // C_)  # HWC rows: channel = index % C
+                z = z + rf if with_res else z
                 yr = F.relu(F.layer_norm(z, (D,), gf, bf_, 1e-5))
                 yr.backward(dy.float())
                 assert (y.float() - yr).abs().max() < 2e-2 * max(1.0, yr.abs().max().item())
-                pairs = [(x.grad, xf.grad), (g.grad, gf.grad), (b.grad, bf_.grad)]
+                pairs = [(x.grad, xf.grad), (g.grad, gf.grad), (b.grad, bf_.grad), (cb.grad, cbf.grad)]
                 if with_res:
                     pairs.append((r.grad, rf.grad))
                 for got, want in pairs:
