@@ -74,3 +74,38 @@ def test_two_rank_sharding_matches_single_process():
         np.testing.assert_allclose(stats, tot, rtol=1e-12)              # every rank sees the global sums
         assert slowest == float(world)                                   # max-over-ranks timing helper
     assert sum(r[7][0] for r in res) == tot[0]
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root]
+    from inversus_b200.policies import InversusCNNPolicy
+    from inversus_b200.ppo_agent import PPOAgent
+    torch.manual_seed(0)
+    agent = PPOAgent(InversusCNNPolicy(), device="cpu")
+    for i, p in enumerate(agent.policy.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    agent._sync_grads()  # the trainer's gradient exchange: one flat all-reduce, then the mean
+    ok = all(torch.allclose(p.grad, torch.full_like(p, (world + 1) / 2 * (i + 1)))
+             for i, p in enumerate(agent.policy.parameters()))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_averages_over_ranks():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
