@@ -146,12 +146,16 @@ class PPOAgent:
     def __init__(self, policy: nn.Module, lr: float = 1e-4, gamma: float = 0.99, lam: float = 0.95,
                  clip_ratio: float = 0.2, epochs: int = 4, batch_size: int = 512, entropy_coef: float = 0.02,
                  value_coef: float = 0.1, device: str = "cpu", *, gae_mode: str = "per_env",
-                 precision: str = "fp32", shuffle: str = "torch", generator: Optional[torch.Generator] = None):
+                 precision: str = "fp32", shuffle: str = "torch", generator: Optional[torch.Generator] = None,
+                 graph_update: bool = False):
         assert gae_mode in ("per_env", "reference") and precision in ("fp32", "bf16") and shuffle in ("torch", "numpy")
         self.device = torch.device(device)
         self.policy = policy.to(self.device)
         # same Adam as the reference (ppo_agent.py:48); on CUDA the single-kernel fused implementation
-        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=lr, fused=self.device.type == "cuda")
+        cuda = self.device.type == "cuda"
+        self.graph_update = bool(graph_update) and cuda  # capture one minibatch step in a CUDA graph
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=lr, fused=cuda, capturable=self.graph_update)
+        self._ug = None  # captured update graph + its static buffers
         self.gamma, self.lam, self.clip_ratio = gamma, lam, clip_ratio
         self.epochs, self.batch_size = epochs, batch_size
         self.entropy_coef, self.value_coef = entropy_coef, value_coef
@@ -250,32 +254,102 @@ class PPOAgent:
             return torch.from_numpy(state["idx"].copy()).to(self.device)
         return torch.randperm(n, device=self.device, generator=self.generator)
 
+    def _minibatch_step(self, idx, fetch, actions, old_log_probs, advantages, returns, sums, validate=True):
+        """One optimisation step on the samples `idx` (ppo_agent.py:198-231); adds the three loss
+        statistics to `sums`. With validate=False it contains no host sync (CUDA-graph capturable)."""
+        grid, extra = fetch(idx)
+        logits, values = self._forward(grid, extra, train=True)
+        dist = torch.distributions.Categorical(logits=logits, validate_args=validate)  # ppo_agent.py:211-213
+        new_log_probs = dist.log_prob(actions[idx])
+        entropy = dist.entropy().mean()
+        ratio = torch.exp(new_log_probs - old_log_probs[idx])
+        adv = advantages[idx]
+        policy_loss = -torch.min(ratio * adv, torch.clamp(ratio, 1.0 - self.clip_ratio, 1.0 + self.clip_ratio) * adv).mean()
+        value_loss = F.mse_loss(values.squeeze(-1), returns[idx])
+        loss = policy_loss + self.value_coef * value_loss - self.entropy_coef * entropy
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        self._sync_grads()
+        torch.nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
+        self.optimizer.step()
+        sums += torch.stack([policy_loss.detach(), value_loss.detach(), entropy.detach()])
+
+    def _update_graph(self, n, fetch, actions, old_log_probs, advantages, returns):
+        """Static buffers + a CUDA graph of one full-size minibatch step (forward, loss, backward,
+        gradient clip, fused Adam). Warm-up steps needed for capture are undone afterwards."""
+        bs = self.batch_size
+        key = (n, bs, id(fetch.__self__) if hasattr(fetch, "__self__") else None)
+        if self._ug is not None and self._ug["n"] == n and self._ug["bs"] == bs:
+            ug = self._ug
+        else:
+            dev = self.device
+            ug = self._ug = {"n": n, "bs": bs, "key": key, "graph": None,
+                             "idx": torch.zeros(bs, dtype=torch.int64, device=dev),
+                             "sums": torch.zeros(3, device=dev),
+                             "actions": torch.empty(n, dtype=torch.int64, device=dev),
+                             "old_lp": torch.empty(n, dtype=torch.float32, device=dev),
+                             "adv": torch.empty(n, dtype=torch.float32, device=dev),
+                             "ret": torch.empty(n, dtype=torch.float32, device=dev)}
+        ug["actions"].copy_(actions)
+        ug["old_lp"].copy_(old_log_probs)
+        ug["adv"].copy_(advantages)
+        ug["ret"].copy_(returns)
+        ug["fetch"] = fetch
+        if ug["graph"] is None:
+            params = list(self.policy.parameters())
+            p_backup = [p.detach().clone() for p in params]
+            o_backup = {p: {k: v.clone() for k, v in st.items() if torch.is_tensor(v)}
+                        for p, st in self.optimizer.state.items()}
+
+            def body():
+                self._minibatch_step(ug["idx"], lambda i: ug["fetch"](i), ug["actions"], ug["old_lp"], ug["adv"],
+                                     ug["ret"], ug["sums"], validate=False)
+            ug["idx"].copy_(torch.arange(bs, device=self.device) % n)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    body()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                body()
+            ug["graph"] = graph
+            with torch.no_grad():  # undo the warm-up/capture steps in place (the graph holds these addresses)
+                for p, b in zip(params, p_backup):
+                    p.copy_(b)
+                for p, st in self.optimizer.state.items():
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            if p in o_backup and k in o_backup[p]:
+                                v.copy_(o_backup[p][k])
+                            else:
+                                v.zero_()
+            ug["sums"].zero_()
+        return ug
+
     def _run_epochs(self, n: int, fetch: Callable[[torch.Tensor], Tuple[torch.Tensor, torch.Tensor]],
                     actions, old_log_probs, advantages, returns) -> Dict[str, float]:
         self.policy.train()
-        sums = torch.zeros(3, device=self.device)
+        distributed = (torch.distributed.is_available() and torch.distributed.is_initialized()
+                       and torch.distributed.get_world_size() > 1)
+        ug = None
+        if self.graph_update and not distributed and self.shuffle == "torch" and n >= self.batch_size:
+            ug = self._update_graph(n, fetch, actions, old_log_probs, advantages, returns)
+            ug["sums"].zero_()
+        sums = ug["sums"] if ug is not None else torch.zeros(3, device=self.device)
         num_updates = 0
         perm_state: dict = {}
         for _ in range(self.epochs):
             perm = self._permutation(n, perm_state)
             for start in range(0, n, self.batch_size):
                 idx = perm[start:start + self.batch_size]
-                grid, extra = fetch(idx)
-                logits, values = self._forward(grid, extra, train=True)
-                dist = torch.distributions.Categorical(logits=logits)  # same ops as ppo_agent.py:211-213
-                new_log_probs = dist.log_prob(actions[idx])
-                entropy = dist.entropy().mean()
-                ratio = torch.exp(new_log_probs - old_log_probs[idx])
-                adv = advantages[idx]
-                policy_loss = -torch.min(ratio * adv, torch.clamp(ratio, 1.0 - self.clip_ratio, 1.0 + self.clip_ratio) * adv).mean()
-                value_loss = F.mse_loss(values.squeeze(-1), returns[idx])
-                loss = policy_loss + self.value_coef * value_loss - self.entropy_coef * entropy
-                self.optimizer.zero_grad(set_to_none=True)
-                loss.backward()
-                self._sync_grads()
-                torch.nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
-                self.optimizer.step()
-                sums += torch.stack([policy_loss.detach(), value_loss.detach(), entropy.detach()])
+                if ug is not None and idx.numel() == self.batch_size:
+                    ug["idx"].copy_(idx)
+                    ug["graph"].replay()
+                else:
+                    self._minibatch_step(idx, fetch, actions, old_log_probs, advantages, returns, sums)
                 num_updates += 1
         if hasattr(self.policy, "mark_updated"):
             self.policy.mark_updated()  # fused optimizers do not bump tensor versions

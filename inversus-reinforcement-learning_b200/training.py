@@ -70,7 +70,8 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
           opponent_difficulty: str = "easy", load_model: Optional[str] = None, *, precision: str = "bf16",
           rollout_steps: Optional[int] = None, batch_size: Optional[int] = None, epochs: int = 4, lr: float = 1e-4,
           reference_gae: bool = False, seed: Optional[int] = None, max_episode_steps: int = 500,
-          save: bool = True, quiet: bool = False, cuda_graph: Optional[bool] = None) -> dict:
+          save: bool = True, quiet: bool = False, cuda_graph: Optional[bool] = None,
+          graph_update: bool = True) -> dict:
     """Shared body of train_vs_dummy / train_selfplay. `num_envs` is the GLOBAL env count; under
     torchrun each rank simulates its shard. Returns a summary dict (steps, episodes, win_rate,
     samples_per_s, ...)."""
@@ -111,7 +112,7 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
     if batch_size is None:
         batch_size = 512 if num_envs * steps_per_env <= 1 << 16 else 16384
     agent = PPOAgent(policy, lr=lr, epochs=epochs, batch_size=batch_size, device=str(dev), precision=precision,
-                     gae_mode="reference" if reference_gae else "per_env")
+                     gae_mode="reference" if reference_gae else "per_env", graph_update=graph_update and world == 1)
     rollout = DeviceRollout(steps_per_env, n_local, dev, store="packed")
     logger = TrainingLogger(log_dir) if rank == 0 else None
 
