@@ -160,6 +160,31 @@ def run_oracle(args, n_envs, steps, warmup, budget_s=None):
     return {"value": n_envs * done_steps / dt, "seconds": dt, "steps": done_steps, "cores": cores}
 
 
+def run_python_loop(args, seconds=4.0, n_envs=64):
+    """The reference's PYTHON step loop, restated in oracle/py_loop.py with the reference's own data
+    structures (pinned to the golden fixtures), timed on ONE host core: the number the north star
+    asks to see beside the GPU result. The live reference measured 6.0e3 env-steps/s on one core of
+    the builder container where this restatement measured 7.7e3."""
+    import numpy as np
+    from oracle.py_loop import PyRunner
+    r = PyRunner(n_envs, args.mode, args.difficulty, args.max_episode_steps, seed=args.seed)
+    rs = np.random.RandomState(args.seed)
+    acts = rs.randint(0, 13, size=(64, n_envs))
+    acts2 = rs.randint(0, 13, size=(64, n_envs)) if args.mode == "selfplay" else None
+    r.reset()
+    for t in range(3):
+        r.step(acts[t], None if acts2 is None else acts2[t], None, auto_reset=True)
+    t0 = time.perf_counter()
+    k = 0
+    while time.perf_counter() - t0 < seconds:
+        r.step(acts[k % 64], None if acts2 is None else acts2[k % 64], None, auto_reset=True)
+        k += 1
+    dt = time.perf_counter() - t0
+    return {"value": n_envs * k / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n_envs} envs x {k} steps ({dt:.1f} s), MultiEnvRunner-style sequential Python loop "
+                      f"(oracle/py_loop.py), fp32 obs built every step, auto-reset"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -177,6 +202,7 @@ def reference_arm(args):
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "python_loop": run_python_loop(args, seconds=3.0),
         "gpu_launches": 0,
         "note": "reference is pure Python (cannot travel to the GPU box); this is its algorithm restated in C "
                 "(oracle/inversus_oracle.c) on all host cores. Python reference measured in the builder "
@@ -419,7 +445,8 @@ def main():
         r = run_oracle(args, nc, 10 ** 9, 3, budget_s=args.cpu_seconds)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"{nc} envs x {r['steps']} steps ({r['seconds']:.1f} s) of the same workload through "
-                         f"oracle/inversus_oracle.c, fp32 obs written every step, {r['cores']} pthreads"}
+                         f"oracle/inversus_oracle.c, fp32 obs written every step, {r['cores']} pthreads",
+               "python_loop": run_python_loop(args, seconds=min(4.0, args.cpu_seconds))}
 
     if rank == 0:
         line = {

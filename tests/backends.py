@@ -97,3 +97,48 @@ class CudaBackend:
         s = self.sim
         return (s.obs.float().cpu().numpy(), s.extra.cpu().numpy(),
                 s.obs_p2.float().cpu().numpy(), s.extra_p2.cpu().numpy())
+
+
+class PyLoopBackend:
+    """The pure-Python restatement (oracle/py_loop.py) as a scenario backend. Checker only."""
+
+    def __init__(self, sc, env_id_base=0):
+        from oracle import py_loop
+        self.pl = py_loop
+        self.r = py_loop.PyRunner(sc["n"], sc["mode"], sc["difficulty"], sc["max_steps"], seed=sc["seed"],
+                                  env_id_base=env_id_base)
+        self.selfplay = sc["mode"] == "selfplay"
+
+    def reset(self, table):
+        self.r.reset(table)
+
+    def step(self, a1, a2, table, auto_reset):
+        return self.r.step(a1, a2, table, auto_reset, both_views=self.selfplay)
+
+    def reset_envs(self, idx, table):
+        for i in idx:
+            self.r.envs[int(i)].reset(None if table is None else table[int(i)])
+
+    def state(self):
+        from oracle.oracle import STATE_DTYPE
+        T = self.pl.Tile
+        out = np.zeros(self.r.n, STATE_DTYPE)
+        for i, e in enumerate(self.r.envs):
+            bits = np.zeros(160, np.uint8)
+            for y in range(10):
+                for x in range(15):
+                    bits[y * 15 + x] = 1 if e.grid[y][x] == T.WHITE else 0
+            out["tiles"][i] = np.packbits(bits, bitorder="little").view(np.uint32)
+            for name, p in (("p1", e.p1), ("p2", e.p2)):
+                out[name][i] = (p.x, p.y, p.ammo, p.reload_counter, int(p.alive))
+            out["n_bullets"][i] = len(e.bullets)
+            for k, b in enumerate(e.bullets):
+                out["bullets"][i, k] = (b.x, b.y, b.dir.value, b.owner)
+            out["step_count"][i] = e.step_count
+            out["episode"][i] = e.episode
+            out["episode_return"][i] = e.episode_return
+        return out
+
+    def obs(self):
+        o1, o2 = self.r.observations(0), self.r.observations(1)
+        return o1[0], o1[1], o2[0], o2[1]
