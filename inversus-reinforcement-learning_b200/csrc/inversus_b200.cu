@@ -39,6 +39,10 @@ struct inv_sim {
     int8_t *h_a1, *h_a2, *d_a1, *d_a2;
     uint32_t *h_status;
     cudaStream_t host_stream;
+    // the small per-env outputs live in ONE device block (extra1, extra2, reward, episode_steps,
+    // episode_return, done, info) so that the *_host calls can fetch them with a single copy
+    char *d_small, *h_small;
+    size_t small_bytes, off_extra1, off_extra2, off_reward, off_steps, off_return, off_done, off_info;
     // host-expand path of inv_step_host (f32 obs only): packed rows device + pinned host staging
     int host_threads;   // 0 = plain DMA of the f32 observation
     double dma_frac;    // share of the envs whose f32 observation is copied directly (rest expanded)
@@ -147,6 +151,7 @@ Params base_params(const inv_sim *s)
 // lock-step). The narrower the observation, the more logic per stored byte, so bf16/u8 step
 // kernels use more logic warps per CTA: E = 64 (bf16, one view) or 128 (bf16 two views, u8).
 constexpr int kTileEnvs = 32;
+constexpr size_t kSmallBlockMax = 4u << 20; // up to 4 MB of small outputs go through one staged copy
 
 template <int OP, int DT, bool P2V, bool INDEXED, int E, int T = kThreads>
 cudaError_t launch_one(const Params &p, int sm_count, cudaStream_t st)
@@ -318,17 +323,28 @@ int inv_create(const inv_config *cfg, inv_sim **out)
     } while (0)
     ALLOC(s->state, (size_t)n * INV_PACKED_STATE_BYTES);
     ALLOC(s->obs1, obs_bytes);
-    ALLOC(s->extra1, (size_t)n * 16);
-    if (p2v) {
-        ALLOC(s->obs2, obs_bytes);
-        ALLOC(s->extra2, (size_t)n * 16);
+    if (p2v) ALLOC(s->obs2, obs_bytes);
+    {
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        size_t o = 0;
+        s->off_extra1 = o; o = up(o + (size_t)n * 16);
+        s->off_extra2 = o; o = up(o + (p2v ? (size_t)n * 16 : 0));
+        s->off_reward = o; o = up(o + (size_t)n * 4);
+        s->off_steps = o; o = up(o + (size_t)n * 4);
+        s->off_return = o; o = up(o + (size_t)n * 8);
+        s->off_done = o; o = up(o + (size_t)n);
+        s->off_info = o; o = up(o + (size_t)n);
+        s->small_bytes = o;
+        ALLOC(s->d_small, s->small_bytes);
+        s->extra1 = reinterpret_cast<float *>(s->d_small + s->off_extra1);
+        s->extra2 = p2v ? reinterpret_cast<float *>(s->d_small + s->off_extra2) : nullptr;
+        s->reward = reinterpret_cast<float *>(s->d_small + s->off_reward);
+        s->ep_steps = reinterpret_cast<int32_t *>(s->d_small + s->off_steps);
+        s->ep_return = reinterpret_cast<double *>(s->d_small + s->off_return);
+        s->done = reinterpret_cast<uint8_t *>(s->d_small + s->off_done);
+        s->info = reinterpret_cast<uint8_t *>(s->d_small + s->off_info);
     }
-    ALLOC(s->reward, (size_t)n * 4);
-    ALLOC(s->done, (size_t)n);
-    ALLOC(s->info, (size_t)n);
     ALLOC(s->dbg, (size_t)n);
-    ALLOC(s->ep_steps, (size_t)n * 4);
-    ALLOC(s->ep_return, (size_t)n * 8);
     ALLOC(s->status, 4);
     ALLOC(s->d_a1, (size_t)n);
     ALLOC(s->d_a2, (size_t)n);
@@ -337,13 +353,10 @@ int inv_create(const inv_config *cfg, inv_sim **out)
     cudaMemset(s->state, 0, (size_t)n * INV_PACKED_STATE_BYTES);
     init_episode_kernel<<<(unsigned)((n + 255) / 256), 256>>>(s->state + 2 * n, n);
     cudaMemset(s->status, 0, 4);
-    cudaMemset(s->reward, 0, (size_t)n * 4);
-    cudaMemset(s->done, 0, (size_t)n);
-    cudaMemset(s->info, 0, (size_t)n);
+    cudaMemset(s->d_small, 0, s->small_bytes);
     cudaMemset(s->dbg, 0, (size_t)n);
-    cudaMemset(s->ep_steps, 0, (size_t)n * 4);
-    cudaMemset(s->ep_return, 0, (size_t)n * 8);
-    if (cudaMallocHost((void **)&s->h_a1, (size_t)n) != cudaSuccess ||
+    if ((s->small_bytes <= kSmallBlockMax && cudaMallocHost((void **)&s->h_small, s->small_bytes) != cudaSuccess) ||
+        cudaMallocHost((void **)&s->h_a1, (size_t)n) != cudaSuccess ||
         cudaMallocHost((void **)&s->h_a2, (size_t)n) != cudaSuccess ||
         cudaMallocHost((void **)&s->h_status, 4) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->host_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -366,10 +379,10 @@ int inv_destroy(inv_sim *s)
     if (!s) return INV_OK;
     DeviceGuard g(s->cfg.device);
     cudaDeviceSynchronize();
-    void *dev[] = {s->state, s->obs1, s->obs2, s->extra1, s->extra2, s->reward, s->done, s->info,
-                   s->dbg, s->ep_steps, s->ep_return, s->status, s->d_a1, s->d_a2};
+    void *dev[] = {s->state, s->obs1, s->obs2, s->d_small, s->dbg, s->status, s->d_a1, s->d_a2};
     for (void *p : dev)
         if (p) cudaFree(p);
+    if (s->h_small) cudaFreeHost(s->h_small);
     if (s->h_a1) cudaFreeHost(s->h_a1);
     if (s->h_a2) cudaFreeHost(s->h_a2);
     if (s->h_status) cudaFreeHost(s->h_status);
@@ -439,10 +452,30 @@ int inv_step(inv_sim *s, const int8_t *a1, const int8_t *a2, void *stream)
     return step_impl(s, a1, a2, stream, nullptr, nullptr);
 }
 
+// After the stream has been synchronised: scatter the staged small-output block to the caller.
+static void scatter_small_outputs(inv_sim *s, float *extra_p1, float *extra_p2, float *reward, uint8_t *done,
+                                  uint8_t *info, int32_t *episode_steps, double *episode_return)
+{
+    if (!s->h_small) return;
+    const size_t n = (size_t)s->n;
+    if (extra_p1) memcpy(extra_p1, s->h_small + s->off_extra1, n * 16);
+    if (extra_p2 && s->extra2) memcpy(extra_p2, s->h_small + s->off_extra2, n * 16);
+    if (reward) memcpy(reward, s->h_small + s->off_reward, n * 4);
+    if (episode_steps) memcpy(episode_steps, s->h_small + s->off_steps, n * 4);
+    if (episode_return) memcpy(episode_return, s->h_small + s->off_return, n * 8);
+    if (done) memcpy(done, s->h_small + s->off_done, n);
+    if (info) memcpy(info, s->h_small + s->off_info, n);
+}
+
 static int copy_small_outputs(inv_sim *s, cudaStream_t st, float *extra_p1, float *extra_p2, float *reward,
                               uint8_t *done, uint8_t *info, int32_t *episode_steps, double *episode_return)
 {
     const int64_t n = s->n;
+    if (extra_p2 && !s->extra2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
+    if (s->h_small) { // small batches: one copy of the whole block, scattered on the host after the sync
+        CUDA_TRY(cudaMemcpyAsync(s->h_small, s->d_small, s->small_bytes, cudaMemcpyDeviceToHost, st));
+        return INV_OK;
+    }
     if (extra_p1) CUDA_TRY(cudaMemcpyAsync(extra_p1, s->extra1, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
     if (extra_p2) {
         if (!s->extra2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
@@ -561,12 +594,14 @@ int inv_step_host(inv_sim *s, const int8_t *a1, const int8_t *a2, void *obs_p1, 
     if (rc != INV_OK) return rc;
     if (expand) {
         // d_bits[0] is always written by the kernel in this mode; only requested views are shipped
-        void *o1 = obs_p1, *o2 = obs_p2;
-        return copy_obs_expand(s, st, o1, o2);
+        rc = copy_obs_expand(s, st, obs_p1, obs_p2); // synchronises the stream
+    } else {
+        rc = copy_obs_plain(s, st, obs_p1, obs_p2);
+        if (rc != INV_OK) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
     }
-    rc = copy_obs_plain(s, st, obs_p1, obs_p2);
     if (rc != INV_OK) return rc;
-    CUDA_TRY(cudaStreamSynchronize(st));
+    scatter_small_outputs(s, extra_p1, extra_p2, reward, done, info, episode_steps, episode_return);
     return INV_OK;
 }
 
@@ -603,6 +638,7 @@ int inv_reset_host(inv_sim *s, void *obs_p1, float *extra_p1, void *obs_p2, floa
     rc = copy_obs_plain(s, st, obs_p1, obs_p2);
     if (rc != INV_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(st));
+    scatter_small_outputs(s, extra_p1, extra_p2, nullptr, nullptr, nullptr, nullptr, nullptr);
     return INV_OK;
 }
 
