@@ -16,7 +16,7 @@ from ._build import build_library
 from ._capi import InversusError, library_path
 
 __all__ = ["constants", "build_library", "library_path", "InversusError", "BatchedInversus",
-           "MultiEnvRunner", "SingleInversusRLEnv", "discrete_to_action", "InfoList",
+           "MultiEnvRunner", "SingleInversusRLEnv", "discrete_to_action", "build_observation", "PlayerId", "InfoList",
            "shard_range", "reduce_rollout_stats", "InversusCNNPolicy", "make_policy_from_env", "PPOAgent",
            "DeviceRollout", "compute_gae", "train_vs_dummy", "train_selfplay"]
 
@@ -25,6 +25,8 @@ _LAZY = {
     "MultiEnvRunner": ("env_wrappers", "MultiEnvRunner"),
     "SingleInversusRLEnv": ("env_wrappers", "SingleInversusRLEnv"),
     "discrete_to_action": ("env_wrappers", "discrete_to_action"),
+    "build_observation": ("env_wrappers", "build_observation"),
+    "PlayerId": ("env_wrappers", "PlayerId"),
     "InfoList": ("env_wrappers", "InfoList"),
     "InversusCNNPolicy": ("policies", "InversusCNNPolicy"),
     "make_policy_from_env": ("policies", "make_policy_from_env"),

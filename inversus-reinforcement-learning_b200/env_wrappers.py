@@ -16,6 +16,7 @@ training.py:150). For throughput use `BatchedInversus` directly (device tensors,
 """
 from __future__ import annotations
 
+import enum
 from collections import namedtuple
 from collections.abc import Sequence
 from typing import Any, Dict, Optional, Tuple
@@ -75,10 +76,31 @@ class InfoList(Sequence):
         return _info_dict(self._b[i], self._s[i], self._r[i])
 
 
-class _BoardDims:
-    """Stands in for `SingleInversusRLEnv.env` where callers only read the board size
-    (policies.py:111-128 make_policy_from_env)."""
+class PlayerId(enum.Enum):
+    """game_types.py:29-32."""
+    P1 = 1
+    P2 = 2
+
+
+class _EngineView:
+    """Stands in for `SingleInversusRLEnv.env` (the reference's InversusEnv): callers read the board
+    size (policies.py:111-128 make_policy_from_env) and pass it to `build_observation`."""
     width, height = BOARD_W, BOARD_H
+
+    def __init__(self, sim, index):
+        self._sim, self._index = sim, index
+
+
+def build_observation(env: "_EngineView", player_id=PlayerId.P1) -> Tuple[np.ndarray, np.ndarray]:
+    """env_wrappers.py:173-245 for one env of a runner: (grid f32[12,10,15], extra f32[4]) from the
+    given player's perspective, rebuilt from the env's current device state (K3 kernel)."""
+    pid = getattr(player_id, "value", player_id)
+    if pid not in (1, 2):
+        raise ValueError(f"Invalid player ID: {player_id}")  # core.py:198
+    sim, i = env._sim, env._index
+    packed = sim.packed_state[:, i:i + 1].contiguous()
+    grid, extra = sim.obs_from_packed(packed, view=pid - 1, obs_dtype="f32")
+    return grid[0].cpu().numpy(), extra[0].cpu().numpy()
 
 
 class _EnvSlot:
@@ -86,7 +108,7 @@ class _EnvSlot:
 
     def __init__(self, runner: "MultiEnvRunner", index: int):
         self._runner, self._index = runner, index
-        self.env = _BoardDims()
+        self.env = _EngineView(runner.sim, index)
         self.opponent_type = runner.opponent_type
         self.difficulty = runner.difficulty
         self.max_episode_steps = runner.max_episode_steps
@@ -176,7 +198,7 @@ class SingleInversusRLEnv:
                  seed: Optional[int] = None, *, device=0):
         self._runner = MultiEnvRunner(1, opponent_type, difficulty, max_episode_steps, seed, device=device)
         self.opponent_type, self.difficulty, self.max_episode_steps = opponent_type, difficulty, max_episode_steps
-        self.env = _BoardDims()
+        self.env = self._runner.envs[0].env
         self._runner.reset()
 
     def reset(self, seed: Optional[int] = None):

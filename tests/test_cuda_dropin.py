@@ -136,3 +136,25 @@ def test_single_env_wrapper():
     assert done and info["episode_steps"] >= 100  # timeout flag stays up until the caller resets
     with pytest.raises(ValueError):
         env.step(13)
+
+
+def test_build_observation_for_both_players():
+    """`build_observation(runner.envs[i].env, PlayerId.P2)` (training.py:10 imports it): both
+    perspectives of one env, equal to what the step wrote / to the oracle's P2 view."""
+    from inversus_b200 import MultiEnvRunner, PlayerId, build_observation
+    r = MultiEnvRunner(5, opponent_type="selfplay", max_episode_steps=50, seed=2)
+    ref = _Ref(5, "selfplay", "easy", 50, 2)
+    g, e = r.reset()
+    ref.reset()
+    rs = np.random.RandomState(0)
+    for _ in range(12):
+        a1, a2 = rs.randint(0, 13, 5), rs.randint(0, 13, 5)
+        (g, e), _, _, _ = r.step(a1, opponent_actions=a2)
+        ref.step(a1, a2, auto_reset=False)
+    for i in range(5):
+        g1, e1 = build_observation(r.envs[i].env, PlayerId.P1)
+        g2, e2 = build_observation(r.envs[i].env, PlayerId.P2)
+        assert np.array_equal(g1, g[i]) and np.array_equal(e1, e[i])
+        assert np.array_equal(g2, ref.obs2[i]) and np.array_equal(e2, ref.extra2[i])
+    with pytest.raises(ValueError):
+        build_observation(r.envs[0].env, 3)
