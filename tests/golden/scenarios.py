@@ -61,7 +61,7 @@ def gen_table(rs, n):
 
 
 def run_scenario(backend, sc, record_obs=True):
-    rs = np.random.RandomState(sc["seed"])
+    rs = np.random.RandomState(sc["seed"] & 0xFFFFFFFF)
     n, T = sc["n"], sc["T"]
     use_table = sc["draws"] == "table"
     selfplay = sc["mode"] == "selfplay"

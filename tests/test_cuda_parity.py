@@ -35,6 +35,8 @@ FRESH = {
     "gpu_table": dict(mode="dummy", difficulty="hard", max_steps=90, n=1000, T=200, seed=205, actions="passive", draws="table", resets="manual"),
     "gpu_ragged": dict(mode="selfplay", difficulty="hard", max_steps=50, n=131, T=120, seed=206, actions="uniform", draws="philox", resets="manual"),
     "gpu_one": dict(mode="dummy", difficulty="hard", max_steps=30, n=1, T=100, seed=207, actions="uniform", draws="philox", resets="auto"),
+    # 64-bit seed (both Philox key words in use) and a large env_id_base (see the test body)
+    "gpu_bigseed": dict(mode="dummy", difficulty="hard", max_steps=45, n=700, T=150, seed=0xDEADBEEFCAFEF00D, actions="uniform", draws="philox", resets="auto"),
 }
 
 
@@ -44,8 +46,9 @@ def test_cuda_matches_oracle_on_fresh_seeds(name):
     observation elements of both views). Sizes include ragged tiles (131, 3000, 1) and > 1 tile."""
     from backends import CudaBackend, OracleBackend
     sc = FRESH[name]
-    want = run_scenario(OracleBackend(sc, nthreads=8), sc)
-    got = run_scenario(CudaBackend(sc), sc)
+    base = 4_000_000_000 if name == "gpu_bigseed" else 0  # global env ids near the top of the u32 range
+    want = run_scenario(OracleBackend(sc, nthreads=8, env_id_base=base), sc)
+    got = run_scenario(CudaBackend(sc, env_id_base=base), sc)
     compare(got, want, float_rtol=1e-6, what=name)
     assert np.array_equal(got["reward_f32"], want["reward_f32"])
     assert np.array_equal(got["episode_return"], want["episode_return"])

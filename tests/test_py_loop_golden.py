@@ -22,3 +22,18 @@ def test_python_loop_reproduces_reference_fixture(name):
     compare(rec, gold, float_rtol=1e-6, what=name)
     assert np.array_equal(rec["reward"], gold["reward"])              # fp64 rewards, exactly
     assert np.array_equal(rec["episode_return"], gold["episode_return"])
+
+
+def test_two_cpu_oracles_agree_on_a_64bit_seed_and_large_env_ids():
+    """The C oracle and the pure-Python loop, written independently, agree with both Philox key
+    words in use and global env ids near the top of the u32 range."""
+    from backends import OracleBackend
+    sc = dict(mode="dummy", difficulty="hard", max_steps=45, n=24, T=150, seed=0xDEADBEEFCAFEF00D,
+              actions="uniform", draws="philox", resets="auto")
+    base = 4_000_000_000
+    a = run_scenario(OracleBackend(sc, env_id_base=base), sc)
+    b = run_scenario(PyLoopBackend(sc, env_id_base=base), sc)
+    compare(a, b, what="bigseed")
+    assert np.array_equal(a["episode_return"], b["episode_return"])
+    other = run_scenario(OracleBackend(dict(sc, seed=0xCAFEF00D), env_id_base=base), sc)
+    assert not np.array_equal(other["state"]["p1"], a["state"]["p1"])  # the high key word matters
