@@ -7,7 +7,9 @@
 //   OP_OBS        K3  observation rebuild from packed-state snapshots (O1)
 //   OP_DEBUG          one engine method at a time (parity tests restating the reference's tests)
 //
-// Execution shape (DESIGN.md "kernel"): a CTA owns a tile of E consecutive envs.
+// Execution shape (DESIGN.md "kernel"): a 128-thread CTA owns a tile of E consecutive envs and the
+// grid is one CTA per tile (E = 32 for fp32 observations: one logic warp, four store warps; 64/128
+// for the narrower step variants -- see launch_e in inversus_b200.cu).
 //   phase 1  thread-per-env: load the 80-byte packed state (5 coalesced 16 B plane loads), run the
 //            integer game logic in registers (+ a private bullet column in shared memory), store
 //            the state back, and leave each env's observation as an 1800-BIT string in shared
