@@ -193,6 +193,13 @@ int inv_set_draw_table(inv_sim *sim, const uint32_t *table_dev);
 int inv_export_state(inv_sim *sim, inv_env_state *out_host, int64_t first, int64_t count);
 int inv_import_state(inv_sim *sim, const inv_env_state *in_host, int64_t first, int64_t count);
 
+/* Resume from a snapshot: copy [5, n] uint4 planes (a copy of INV_BUF_PACKED_STATE taken earlier
+ * from a handle with the same n_envs) into the handle. Together with the seed this restores the
+ * whole simulation: every later draw is a pure function of (seed, global env id, episode,
+ * step_count, k), all of which live in the packed state. The observation buffers are NOT
+ * refreshed; call inv_obs_from_packed on the handle's own state (or step) to get them. */
+int inv_load_packed_state(inv_sim *sim, const void *packed_dev, void *stream);
+
 /* Rebuild observations from packed-state snapshots (build_observation, env_wrappers.py:173-245,
  * over data copied earlier from INV_BUF_PACKED_STATE): a PPO rollout keeps 80 B/env-step instead
  * of 7216 B and decodes minibatches on demand. packed_dev: [5, stride] uint4 planes, entries

@@ -66,6 +66,7 @@ SYMBOLS = {
     "inv_set_draw_table": (C.c_int, [C.c_void_p, C.c_void_p]),
     "inv_export_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
     "inv_import_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
+    "inv_load_packed_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "inv_obs_from_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "inv_debug_phase": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -727,6 +727,16 @@ int inv_import_state(inv_sim *s, const inv_env_state *in, int64_t first, int64_t
     return INV_OK;
 }
 
+int inv_load_packed_state(inv_sim *s, const void *packed_dev, void *stream)
+{
+    if (!s || !packed_dev) return fail(INV_ERR_INVALID_ARG, "inv_load_packed_state: null argument");
+    DeviceGuard g(s->cfg.device);
+    CUDA_TRY(cudaMemcpyAsync(s->state, packed_dev, (size_t)s->n * INV_PACKED_STATE_BYTES, cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    s->was_reset = true;
+    return INV_OK;
+}
+
 int inv_obs_from_packed(inv_sim *s, const void *packed_dev, int64_t stride, int64_t count, int view, int obs_dtype,
                         void *obs_out, float *extra_out, void *stream)
 {

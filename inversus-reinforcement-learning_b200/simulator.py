@@ -261,6 +261,19 @@ class BatchedInversus:
         """Copy of the packed state planes ([5, N, 4] int32 = 80 B/env): what a rollout stores."""
         return self.packed_state.clone()
 
+    def restore(self, packed: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Resume from `snapshot()`: loads the packed planes and rewrites the observation buffers.
+        With the same seed the continuation is bit-identical to the run the snapshot came from
+        (every draw is a function of seed, env id, episode, step and draw index)."""
+        assert packed.is_cuda and packed.is_contiguous() and tuple(packed.shape) == (5, self.num_envs, 4)
+        _capi.check(self._lib.inv_load_packed_state(self._h.ptr, packed.data_ptr(), _stream_ptr(self.device)))
+        for view, (o, e) in enumerate(((self.obs, self.extra), (self.obs_p2, self.extra_p2))):
+            if o is not None:
+                _capi.check(self._lib.inv_obs_from_packed(self._h.ptr, self.packed_state.data_ptr(), self.num_envs,
+                                                          self.num_envs, view, self._dt, o.data_ptr(), e.data_ptr(),
+                                                          _stream_ptr(self.device)))
+        return self.obs, self.extra
+
     def obs_from_packed(self, packed: torch.Tensor, view: int = 0, obs_dtype: Optional[str] = None,
                         count: Optional[int] = None):
         """Rebuild (obs, extra) from packed-state snapshots ([5, M, 4] int32 planes)."""
