@@ -3,7 +3,7 @@ metrics (training_log.csv: step, episode, avg_reward, win_rate, avg_ep_len, loss
 ships two such logs (runs/*/training_log.csv: 0.35 win rate vs the easy dummy after 200 k steps,
 0.57 vs the hard dummy after 500 k more); this produces ours for the same opponents.
 
-    python profiles/learning_run.py easy|hard [total_updates]
+    python profiles/learning_run.py easy|hard|selfplay [total_updates]
 """
 import json
 import os
@@ -21,8 +21,9 @@ updates = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 num_envs, rollout_steps = 16384, 64
 torch.manual_seed(0)
 log_dir = f"/tmp/inv_learning_{difficulty}"
-out = train("vs_dummy", num_envs=num_envs, total_steps=num_envs * rollout_steps * updates, log_dir=log_dir,
-            opponent_difficulty=difficulty, precision="bf16", rollout_steps=rollout_steps, batch_size=8192,
+mode = "selfplay" if difficulty == "selfplay" else "vs_dummy"
+out = train(mode, num_envs=num_envs, total_steps=num_envs * rollout_steps * updates, log_dir=log_dir,
+            opponent_difficulty="easy" if mode == "selfplay" else difficulty, precision="bf16", rollout_steps=rollout_steps, batch_size=8192,
             epochs=4, lr=1e-4, seed=0, quiet=False, save=False)
 dst = os.path.join(ROOT, "gpurun_out", f"learning_{difficulty}_training_log.csv")
 os.makedirs(os.path.dirname(dst), exist_ok=True)
