@@ -73,6 +73,7 @@ typedef enum { INV_OBS_F32 = 0, INV_OBS_BF16 = 1, INV_OBS_U8 = 2 } inv_obs_dtype
 /* sticky device status bits (inv_poll_status) */
 #define INV_STATUS_INVALID_ACTION 1u
 #define INV_STATUS_BULLET_OVERFLOW 2u
+#define INV_STATUS_BAD_INDEX 4u /* inv_reset_envs saw an index outside [0, n_envs): that entry was skipped */
 
 typedef struct inv_sim inv_sim;
 

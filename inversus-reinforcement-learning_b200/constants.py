@@ -27,7 +27,7 @@ THRESH_RANDMOVE_HARD = 214748365   # u < 0.05   (env_wrappers.py:89,105)
 THRESH_MOVE_EASY = 4294968         # not (u > 0.001)  (env_wrappers.py:82,123)
 
 INFO_LANDED_HIT, INFO_GOT_HIT, INFO_WIN, INFO_LOSE = 1, 2, 4, 8
-STATUS_INVALID_ACTION, STATUS_BULLET_OVERFLOW = 1, 2
+STATUS_INVALID_ACTION, STATUS_BULLET_OVERFLOW, STATUS_BAD_INDEX = 1, 2, 4
 
 # algorithmic HBM bytes per env-step of the fused step kernel (DESIGN.md "roofline")
 STATE_RW_BYTES = 2 * PACKED_STATE_BYTES

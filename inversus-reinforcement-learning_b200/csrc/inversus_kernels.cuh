@@ -554,7 +554,16 @@ __global__ void __launch_bounds__(T) inv_kernel(const Params p)
         const int nvalid = (int)min((int64_t)E, p.count - base);
 
         // ------------------------------------------------------------ phase 1: thread per env
-        if (tid < nvalid) {
+        bool live = tid < nvalid;
+        if (INDEXED && live) { // a bad index must not become an out-of-bounds write
+            const int64_t cand = p.idx[base + tid];
+            if ((uint64_t)cand >= (uint64_t)p.stride) {
+                atomicOr(p.status, INV_STATUS_BAD_INDEX);
+                s_env[tid] = -1;
+                live = false;
+            }
+        }
+        if (live) {
             const int64_t ei = INDEXED ? p.idx[base + tid] : base + tid;
             if (INDEXED) s_env[tid] = ei;
             uint16_t *sb = sbul + tid;
@@ -712,6 +721,7 @@ __global__ void __launch_bounds__(T) inv_kernel(const Params p)
                     const int e = g / Fmt::kChunks;
                     const int c = g - e * Fmt::kChunks;
                     const int bit = c * Fmt::kBits;
+                    if (s_env[e] < 0) continue; // rejected index
                     const uint32_t w = rows[e * kRowWords + (bit >> 5)] >> (bit & 31);
                     st_stream(out + s_env[e] * Fmt::kChunks + c, Fmt::expand(w));
                 }
@@ -734,6 +744,7 @@ __global__ void __launch_bounds__(T) inv_kernel(const Params p)
                     w.z = (4 * c + 2 < kRowWords) ? r[2] : 0u;
                     w.w = (4 * c + 3 < kRowWords) ? r[3] : 0u;
                     const int64_t eo = INDEXED ? s_env[e] : base + e;
+                    if (INDEXED && eo < 0) continue;
                     out[eo * 16 + c] = w;
                 }
             }

@@ -300,3 +300,18 @@ def test_snapshot_restore_resumes_bit_identically(mode):
         a2.restore(snap)
         a2.step(acts[20])
         assert not torch.equal(c.packed_state, a2.packed_state)
+
+
+def test_out_of_range_reset_indices_are_rejected_not_written():
+    import torch
+    from inversus_b200 import BatchedInversus
+    from inversus_b200.constants import STATUS_BAD_INDEX
+    s = BatchedInversus(100, "dummy", "hard", 50, seed=1, auto_reset=False)
+    s.reset()
+    before, obs_before = s.packed_state.clone(), s.obs.clone()
+    s.reset_envs(torch.tensor([3, 100, -1, 10 ** 12, 7], dtype=torch.int64))
+    assert s.poll_status() & STATUS_BAD_INDEX
+    changed = (s.packed_state != before).any(dim=(0, 2)).nonzero().flatten().tolist()
+    assert changed == [3, 7]
+    keep = [i for i in range(100) if i not in (3, 7)]
+    assert torch.equal(s.obs[keep], obs_before[keep])
