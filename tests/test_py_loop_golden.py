@@ -37,3 +37,20 @@ def test_two_cpu_oracles_agree_on_a_64bit_seed_and_large_env_ids():
     assert np.array_equal(a["episode_return"], b["episode_return"])
     other = run_scenario(OracleBackend(dict(sc, seed=0xCAFEF00D), env_id_base=base), sc)
     assert not np.array_equal(other["state"]["p1"], a["state"]["p1"])  # the high key word matters
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_two_cpu_oracles_agree_on_random_configurations(case):
+    """Differential test between the two independently written CPU restatements (C and pure
+    Python) over random modes, difficulties, timeouts, action mixes, draw sources and reset
+    policies -- beyond the committed fixtures."""
+    from backends import OracleBackend
+    rs = np.random.RandomState(1000 + case)
+    sc = dict(mode=["dummy", "selfplay"][rs.randint(2)], difficulty=["easy", "hard"][rs.randint(2)],
+              max_steps=int(rs.choice([7, 33, 120, 500])), n=int(rs.randint(3, 20)), T=int(rs.randint(60, 160)),
+              seed=int(rs.randint(0, 2**31)), actions=["uniform", "charge", "passive", "shooty"][rs.randint(4)],
+              draws=["philox", "table"][rs.randint(2)], resets=["auto", "manual"][rs.randint(2)])
+    a = run_scenario(OracleBackend(sc), sc)
+    b = run_scenario(PyLoopBackend(sc), sc)
+    compare(a, b, what=str(sc))
+    assert np.array_equal(a["episode_return"], b["episode_return"])
