@@ -22,7 +22,11 @@
 // Reference behaviour is cited as file:line of Jason-Hoford/inversus-reinforcement-learning.
 #pragma once
 
+#ifdef INV_HOST_BUILD
+#include "host_shim.h" // tests/host_kernel: compiles the game logic below for the CPU (test harness only)
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "../../include/inversus_b200.h"
@@ -492,6 +496,94 @@ __device__ __forceinline__ void build_row(uint32_t *row, const Env &s, const uin
     }
 }
 
+// ---- the wrapper step as one function (also compiled for the host by tests/host_kernel) ----
+
+struct StepResult {
+    float reward;      // env_wrappers.py:525 (binary64 sum rounded to float32)
+    uint8_t done, info;
+    int32_t ep_steps;  // info["episode_steps"], before any auto-reset
+    double ep_return;  // info["episode_return"]
+};
+
+// env_wrappers.py:272-284 (+ core.py:55-154): a new episode in place.
+__device__ __forceinline__ void rl_reset(Env &s, const Params &p, uint32_t gid, const uint32_t *trow)
+{
+    s.episode += 1u;
+    Draws dr;
+    dr.init(p, gid, s.episode, INV_STREAM_RESET, trow ? trow + INV_TABLE_RESET_OFF : nullptr);
+    engine_reset(s, dr);
+    s.step = 0u;
+    s.ret = 0.0;
+}
+
+// env_wrappers.py:286-444 for one env: P2's action (scripted, or given in selfplay mode), engine tick,
+// reward shaping, done/timeout, and -- with auto_reset -- the trainer's reset-on-done
+// (training.py:148-151). Ids outside 0..12 raise the sticky status bit and act as NONE.
+template <int E>
+__device__ __forceinline__ StepResult rl_step(Env &s, uint16_t *sb, int a1, int a2, const Params &p, uint32_t gid,
+                                              const uint32_t *trow)
+{
+    if ((unsigned)a1 > 12u) { atomicOr(p.status, INV_STATUS_INVALID_ACTION); a1 = 0; }
+    if (p.mode == INV_MODE_DUMMY) { // env_wrappers.py:305-306
+        Draws dr;
+        dr.init(p, gid, s.episode, s.step, trow);
+        a2 = dummy_policy(s, dr, p.difficulty);
+    } else if ((unsigned)a2 > 12u) { // :307-314, the caller ran opponent_policy
+        atomicOr(p.status, INV_STATUS_INVALID_ACTION);
+        a2 = 0;
+    }
+    const int prev_alive0 = s.alive[0], prev_alive1 = s.alive[1]; // :319-320
+    const int white0 = count_white(s);                            // :328-329
+    step_players<E>(s, sb, a1, a2, p.status);                     // :332
+    s.step += 1u;                                                 // :333
+
+    // reward shaping in binary64, in the reference's order (env_wrappers.py:343-438);
+    // _rn intrinsics keep nvcc from contracting mul+add into fma.
+    double r = 0.0;
+    uint32_t info = 0u;
+    const int diff = count_white(s) - white0;
+    if (diff > 0) r = __dadd_rn(r, __dmul_rn((double)diff, 0.01));                          // :352-354
+    if (prev_alive1 && !s.alive[1]) { r = __dadd_rn(r, 1.0); info |= INV_INFO_LANDED_HIT; } // :357-360
+    if (prev_alive0 && !s.alive[0]) { r = __dadd_rn(r, -0.01); info |= INV_INFO_GOT_HIT; }  // :364-367
+    if (s.alive[0] && s.ammo[0] == 0) r = __dadd_rn(r, -0.001);                             // :372-373
+    if (s.alive[0] && s.alive[1]) {                                                         // :377-405
+        const int dist = abs(s.x[0] - s.x[1]) + abs(s.y[0] - s.y[1]);
+        r = __dadd_rn(r, kProximity[dist]); // 0.002 * (1 - dist / 25), dist <= 23
+        const bool aligned = (s.x[0] == s.x[1]) || (s.y[0] == s.y[1]);
+        if (aligned) r = __dadd_rn(r, 0.002);
+        if (a1 >= 5 && aligned && s.ammo[0] > 0) {
+            const int sd = (a1 - 5) & 3;
+            bool aim = false;
+            if (s.x[0] == s.x[1]) aim = (s.y[0] < s.y[1] && sd == 2) || (s.y[0] > s.y[1] && sd == 0);
+            else                  aim = (s.x[0] < s.x[1] && sd == 1) || (s.x[0] > s.x[1] && sd == 3);
+            if (aim) r = __dadd_rn(r, 0.05);
+        }
+    }
+    bool done = false;
+    const bool over = !(s.alive[0] && s.alive[1]);                                          // core.py:477-481
+    if (over) {                                                                             // :408-422
+        done = true;
+        if (s.alive[0]) { r = __dadd_rn(r, 10.0); info |= INV_INFO_WIN; }
+        else if (s.alive[1]) { r = __dadd_rn(r, -0.1); info |= INV_INFO_LOSE; }
+    } else {
+        r = __dadd_rn(r, -0.001);                                                           // :425
+    }
+    if (s.step >= (uint32_t)p.max_steps) {                                                  // :434-438
+        done = true;
+        if (!over) r = __dadd_rn(r, -2.0);
+    }
+    s.ret = __dadd_rn(s.ret, r);                                                            // :440
+    StepResult o;
+    o.reward = __double2float_rn(r);
+    o.done = done ? 1 : 0;
+    o.info = (uint8_t)info;
+    o.ep_steps = (int32_t)s.step;
+    o.ep_return = s.ret;
+    if (done && p.auto_reset) rl_reset(s, p, gid, trow);                                    // training.py:148-151
+    return o;
+}
+
+#ifndef INV_HOST_BUILD
 // ---- observation formats: how many store chunks per env and how a chunk is expanded ----
 template <int DT> struct ObsFmt;
 template <> struct ObsFmt<INV_OBS_F32> {  // 1800 f32 = 450 x 16 B, 4 bits per chunk
@@ -574,78 +666,14 @@ __global__ void __launch_bounds__(T) inv_kernel(const Params p)
             const uint32_t *trow = p.table ? p.table + ei * INV_TABLE_STRIDE : nullptr;
 
             if (OP == OP_STEP) {
-                int a1 = p.a1[ei];
-                if ((unsigned)a1 > 12u) { atomicOr(p.status, INV_STATUS_INVALID_ACTION); a1 = 0; }
-                int a2;
-                if (p.mode == INV_MODE_DUMMY) { // env_wrappers.py:305-306
-                    Draws dr;
-                    dr.init(p, gid, s.episode, s.step, trow);
-                    a2 = dummy_policy(s, dr, p.difficulty);
-                } else {                        // :307-314, the caller ran opponent_policy
-                    a2 = p.a2[ei];
-                    if ((unsigned)a2 > 12u) { atomicOr(p.status, INV_STATUS_INVALID_ACTION); a2 = 0; }
-                }
-                const int prev_alive0 = s.alive[0], prev_alive1 = s.alive[1]; // :319-320
-                const int white0 = count_white(s);                            // :328-329
-                step_players<E>(s, sb, a1, a2, p.status);                     // :332
-                s.step += 1u;                                                 // :333
-
-                // reward shaping in binary64, in the reference's order (env_wrappers.py:343-438);
-                // _rn intrinsics keep nvcc from contracting mul+add into fma.
-                double r = 0.0;
-                uint32_t info = 0u;
-                const int diff = count_white(s) - white0;
-                if (diff > 0) r = __dadd_rn(r, __dmul_rn((double)diff, 0.01));                     // :352-354
-                if (prev_alive1 && !s.alive[1]) { r = __dadd_rn(r, 1.0); info |= INV_INFO_LANDED_HIT; } // :357-360
-                if (prev_alive0 && !s.alive[0]) { r = __dadd_rn(r, -0.01); info |= INV_INFO_GOT_HIT; }  // :364-367
-                if (s.alive[0] && s.ammo[0] == 0) r = __dadd_rn(r, -0.001);                        // :372-373
-                if (s.alive[0] && s.alive[1]) {                                                    // :377-405
-                    const int dist = abs(s.x[0] - s.x[1]) + abs(s.y[0] - s.y[1]);
-                    r = __dadd_rn(r, kProximity[dist]); // 0.002 * (1 - dist / 25), dist <= 23
-                    const bool aligned = (s.x[0] == s.x[1]) || (s.y[0] == s.y[1]);
-                    if (aligned) r = __dadd_rn(r, 0.002);
-                    if (a1 >= 5 && aligned && s.ammo[0] > 0) {
-                        const int sd = (a1 - 5) & 3;
-                        bool aim = false;
-                        if (s.x[0] == s.x[1]) aim = (s.y[0] < s.y[1] && sd == 2) || (s.y[0] > s.y[1] && sd == 0);
-                        else                  aim = (s.x[0] < s.x[1] && sd == 1) || (s.x[0] > s.x[1] && sd == 3);
-                        if (aim) r = __dadd_rn(r, 0.05);
-                    }
-                }
-                bool done = false;
-                const bool over = !(s.alive[0] && s.alive[1]);                                     // core.py:477-481
-                if (over) {                                                                        // :408-422
-                    done = true;
-                    if (s.alive[0]) { r = __dadd_rn(r, 10.0); info |= INV_INFO_WIN; }
-                    else if (s.alive[1]) { r = __dadd_rn(r, -0.1); info |= INV_INFO_LOSE; }
-                } else {
-                    r = __dadd_rn(r, -0.001);                                                      // :425
-                }
-                if (s.step >= (uint32_t)p.max_steps) {                                             // :434-438
-                    done = true;
-                    if (!over) r = __dadd_rn(r, -2.0);
-                }
-                s.ret = __dadd_rn(s.ret, r);                                                       // :440
-                p.reward[ei] = __double2float_rn(r);                                               // :525
-                p.done[ei] = done ? 1 : 0;
-                p.info[ei] = (uint8_t)info;
-                p.ep_steps[ei] = (int32_t)s.step;
-                p.ep_return[ei] = s.ret;
-                if (done && p.auto_reset) {                                                        // training.py:148-151
-                    s.episode += 1u;
-                    Draws dr;
-                    dr.init(p, gid, s.episode, INV_STREAM_RESET, trow ? trow + INV_TABLE_RESET_OFF : nullptr);
-                    engine_reset(s, dr);
-                    s.step = 0u;
-                    s.ret = 0.0;
-                }
+                const StepResult o = rl_step<E>(s, sb, p.a1[ei], p.mode == INV_MODE_DUMMY ? 0 : p.a2[ei], p, gid, trow);
+                p.reward[ei] = o.reward;                                                           // env_wrappers.py:525
+                p.done[ei] = o.done;
+                p.info[ei] = o.info;
+                p.ep_steps[ei] = o.ep_steps;
+                p.ep_return[ei] = o.ep_return;
             } else if (OP == OP_RESET) { // env_wrappers.py:272-284
-                s.episode += 1u;
-                Draws dr;
-                dr.init(p, gid, s.episode, INV_STREAM_RESET, trow ? trow + INV_TABLE_RESET_OFF : nullptr);
-                engine_reset(s, dr);
-                s.step = 0u;
-                s.ret = 0.0;
+                rl_reset(s, p, gid, trow);
             } else if (OP == OP_DEBUG) {
                 int res = 0;
                 switch (p.phase) {
@@ -752,5 +780,7 @@ __global__ void __launch_bounds__(T) inv_kernel(const Params p)
         __syncthreads(); // the tile's shared rows are reused by the next iteration
     }
 }
+
+#endif // INV_HOST_BUILD
 
 } // namespace inv

@@ -142,3 +142,102 @@ class PyLoopBackend:
     def obs(self):
         o1, o2 = self.r.observations(0), self.r.observations(1)
         return o1[0], o1[1], o2[0], o2[1]
+
+
+class HostKernelBackend:
+    """The PRODUCT's own step logic (csrc/inversus_kernels.cuh: load_env, rl_step, rl_reset,
+    build_row, store_env) compiled for the host through tests/host_kernel/host_shim.h and driven
+    over the same packed-state planes the GPU uses. Test harness only: it lets the CPU suite replay
+    the golden fixtures through the real kernel logic without a GPU."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            import os
+            import subprocess
+            here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_kernel")
+            so = os.path.join(here, "libhost_kernel.so")
+            srcs = [os.path.join(here, "harness.cpp"), os.path.join(here, "host_shim.h"),
+                    os.path.join(os.path.dirname(here), "..", "inversus-reinforcement-learning_b200", "csrc",
+                                 "inversus_kernels.cuh")]
+            if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+                subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+                                       "-Wno-unknown-pragmas", "-I", here, "-o", so, srcs[0]])
+            cls._lib = C.CDLL(so)
+        return cls._lib
+
+    def __init__(self, sc, env_id_base=0):
+        self.n = sc["n"]
+        self.mode = {"dummy": 0, "selfplay": 1}[sc["mode"]]
+        self.diff = {"easy": 0, "hard": 1}[sc["difficulty"]]
+        self.max_steps, self.seed, self.base = sc["max_steps"], sc["seed"], env_id_base
+        self.selfplay = sc["mode"] == "selfplay"
+        n = self.n
+        self.planes = np.zeros((5, n, 4), np.uint32)
+        self.planes[2, :, 0] = 0xFFFFFFFF  # "no episode yet", like inv_create
+        self.obs1 = np.zeros((n, 12, 10, 15), np.float32)
+        self.obs2 = np.zeros((n, 12, 10, 15), np.float32)
+        self.extra1 = np.zeros((n, 4), np.float32)
+        self.extra2 = np.zeros((n, 4), np.float32)
+        self.status = np.zeros(1, np.uint32)
+
+    @staticmethod
+    def _p(a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    def _reset(self, idx, table):
+        t = None if table is None else np.ascontiguousarray(table, np.uint32)
+        i = None if idx is None else np.ascontiguousarray(idx, np.int64)
+        self.lib().hk_reset(self._p(self.planes), C.c_int64(self.n), self._p(i), C.c_int64(0 if i is None else len(i)),
+                            C.c_uint64(self.seed), C.c_uint32(self.base), self._p(t), self._p(self.obs1),
+                            self._p(self.extra1), self._p(self.obs2), self._p(self.extra2), self._p(self.status))
+
+    def reset(self, table):
+        self._reset(None, table)
+
+    def reset_envs(self, idx, table):
+        self._reset(idx, table)
+
+    def step(self, a1, a2, table, auto_reset):
+        n = self.n
+        a1 = np.ascontiguousarray(a1, np.int8)
+        a2 = None if a2 is None else np.ascontiguousarray(a2, np.int8)
+        t = None if table is None else np.ascontiguousarray(table, np.uint32)
+        out = dict(reward=np.zeros(n, np.float32), done=np.zeros(n, np.uint8), flags=np.zeros(n, np.uint8),
+                   episode_steps=np.zeros(n, np.int32), episode_return=np.zeros(n, np.float64))
+        self.lib().hk_step(self._p(self.planes), C.c_int64(n), self._p(a1), self._p(a2), self._p(t), self.mode,
+                           self.diff, self.max_steps, int(auto_reset), C.c_uint64(self.seed), C.c_uint32(self.base),
+                           self._p(self.obs1), self._p(self.extra1), self._p(self.obs2), self._p(self.extra2),
+                           self._p(out["reward"]), self._p(out["done"]), self._p(out["flags"]),
+                           self._p(out["episode_steps"]), self._p(out["episode_return"]), self._p(self.status))
+        assert self.status[0] == 0
+        out["obs1"], out["extra1"] = self.obs1, self.extra1
+        if self.selfplay:
+            out["obs2"], out["extra2"] = self.obs2, self.extra2
+        return out
+
+    def state(self):
+        """Unpack the planes into the canonical state array."""
+        from oracle.oracle import STATE_DTYPE
+        pl, n = self.planes, self.n
+        out = np.zeros(n, STATE_DTYPE)
+        out["tiles"][:, :4] = pl[0]
+        out["tiles"][:, 4] = pl[1, :, 0]
+        for name, w in (("p1", pl[1, :, 1]), ("p2", pl[1, :, 2])):
+            out[name] = np.stack([w & 15, (w >> 4) & 15, (w >> 8) & 7, (w >> 11) & 31, (w >> 16) & 1], axis=1)
+        nb = (pl[1, :, 1] >> 20) & 31
+        out["n_bullets"] = nb
+        out["step_count"] = pl[1, :, 3].astype(np.int32)
+        out["episode"] = pl[2, :, 0]
+        out["episode_return"] = (pl[2, :, 1].astype(np.uint64) | (pl[2, :, 2].astype(np.uint64) << np.uint64(32))).view(np.float64)
+        words = np.concatenate([pl[3], pl[4]], axis=1)  # [n, 8]
+        for s in range(16):
+            b = (words[:, s >> 1] >> ((s & 1) * 16)) & 0xFFFF
+            live = s < nb
+            out["bullets"][:, s] = np.where(live[:, None], np.stack([b & 15, (b >> 4) & 15, (b >> 8) & 3, (b >> 10) & 1], 1), 0)
+        return out
+
+    def obs(self):
+        return self.obs1, self.extra1, self.obs2, self.extra2
