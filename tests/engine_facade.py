@@ -291,3 +291,147 @@ class CudaEngine:
         self._push()
         g, e = self.sim.obs_from_packed(self.sim.snapshot(), view=viewer, obs_dtype="f32")
         return g[0].cpu().numpy(), e[0].cpu().numpy()
+
+
+class HostKernelEngine:
+    """The product's engine functions compiled for the host (tests/host_kernel) behind core.py's
+    method names: the CPU-side twin of CudaEngine, same device functions, no GPU needed."""
+
+    def __init__(self, width=15, height=10, seed=1234):
+        import ctypes as C_
+        import numpy as np
+        from backends import HostKernelBackend
+        assert width <= 15 and height <= 10
+        self.C, self.np = C_, np
+        self.lib = HostKernelBackend.lib()
+        self.b = HostKernelBackend(dict(n=1, mode="selfplay", difficulty="hard", max_steps=500, seed=seed))
+        self.width, self.height = 15, 10
+        self.player_color = BLACK
+        self.b.reset(None)
+
+    # packed-plane accessors (DESIGN.md section 3)
+    def _pw(self, i):
+        return int(self.b.planes[1, 0, 1 + i])
+
+    def _set_pw(self, i, w):
+        self.b.planes[1, 0, 1 + i] = w
+
+    def _pv(self, i):
+        fields = {"x": (0, 15), "y": (4, 15), "ammo": (8, 7), "reload_counter": (11, 31), "alive": (16, 1)}
+
+        def get(k):
+            sh, m = fields[k]
+            return (self._pw(i) >> sh) & m
+
+        def set_(k, v):
+            sh, m = fields[k]
+            self._set_pw(i, (self._pw(i) & ~(m << sh)) | ((int(v) & m) << sh))
+        return _PlayerView(get, set_)
+
+    @property
+    def player1(self):
+        return self._pv(0)
+
+    @property
+    def player2(self):
+        return self._pv(1)
+
+    player_x = property(lambda s: s.player1.x, lambda s, v: setattr(s.player1, "x", v))
+
+    @property
+    def player_y(self):
+        return self.player1.y
+
+    @player_y.setter
+    def player_y(self, v):
+        self.player1.y = v
+        self.bullets = []  # core.py:180-181
+
+    @property
+    def bullets(self):
+        n = (self._pw(0) >> 20) & 31
+        words = [int(w) for w in list(self.b.planes[3, 0]) + list(self.b.planes[4, 0])]
+        out = []
+        for s in range(n):
+            b = (words[s >> 1] >> ((s & 1) * 16)) & 0xFFFF
+            out.append(Bullet(b & 15, (b >> 4) & 15, (b >> 8) & 3, (b >> 10) & 1))
+        return out
+
+    @bullets.setter
+    def bullets(self, lst):
+        words = [0] * 8
+        for s, b in enumerate(lst):
+            words[s >> 1] |= (b.x | (b.y << 4) | (b.dir << 8) | (b.owner << 10)) << ((s & 1) * 16)
+        self.b.planes[3, 0] = words[:4]
+        self.b.planes[4, 0] = words[4:]
+        self._set_pw(0, (self._pw(0) & ~(31 << 20)) | (len(lst) << 20))
+
+    def get_bullets(self):
+        return self.bullets
+
+    def _tile_word(self, i):
+        return (0, i >> 5) if (i >> 5) < 4 else (1, 0)
+
+    def _get_tile(self, x, y):
+        if not (0 <= x < self.width and 0 <= y < self.height):
+            raise IndexError
+        i = y * 15 + x
+        pl, w = self._tile_word(i)
+        return (int(self.b.planes[pl, 0, w]) >> (i & 31)) & 1
+
+    def _set_tile(self, x, y, c):
+        if not (0 <= x < self.width and 0 <= y < self.height):
+            raise IndexError
+        i = y * 15 + x
+        pl, w = self._tile_word(i)
+        v = int(self.b.planes[pl, 0, w])
+        self.b.planes[pl, 0, w] = (v | (1 << (i & 31))) if c else (v & ~(1 << (i & 31)))
+
+    def _call(self, phase, pid=0, arg=0, arg2=0):
+        C_, np = self.C, self.np
+        res = np.zeros(1, np.uint8)
+        rc = self.lib.hk_debug(self.b.planes.ctypes.data_as(C_.c_void_p), C_.c_int64(1), phase, pid, arg, arg2, 1,
+                               C_.c_uint64(self.b.seed), C_.c_uint32(0), res.ctypes.data_as(C_.c_void_p),
+                               self.b.status.ctypes.data_as(C_.c_void_p))
+        assert rc == 0 and self.b.status[0] == 0
+        return int(res[0])
+
+    def reset(self):
+        self._call(6)
+
+    def try_move_player(self, d, pid=P1):
+        return bool(self._call(0, pid, d))
+
+    def spawn_bullet(self, d, pid=P1):
+        return bool(self._call(1, pid, d))
+
+    def spawn_wide_shot(self, pid, d):
+        return bool(self._call(2, pid, d))
+
+    def _reload_ammo(self):
+        self._call(3)
+
+    def update_bullets(self):
+        self._call(4)
+
+    def step_players(self, a1, a2):
+        self._call(5, 0, a1, a2)
+
+    def step(self, a1):
+        self.step_players(a1, NONE)
+
+    def is_round_over(self):
+        return not (self.player1.alive and self.player2.alive)
+
+    def get_winner(self):
+        a1, a2 = self.player1.alive, self.player2.alive
+        if a1 and a2:
+            return None
+        return P2 if (a2 and not a1) else (P1 if (a1 and not a2) else None)
+
+    def observation(self, viewer=P1):
+        C_, np = self.C, self.np
+        g, e = np.zeros((12, 10, 15), np.float32), np.zeros(4, np.float32)
+        self.lib.hk_observation(self.b.planes.ctypes.data_as(C_.c_void_p), C_.c_int64(1), C_.c_int64(0), viewer,
+                                g.ctypes.data_as(C_.c_void_p), e.ctypes.data_as(C_.c_void_p))
+        return g, e

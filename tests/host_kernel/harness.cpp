@@ -80,6 +80,56 @@ int hk_step(uint32_t *planes, int64_t n, const int8_t *a1, const int8_t *a2, con
     return 0;
 }
 
+// One engine method of core.py on env 0..n-1, like inv_debug_phase (same dispatch, same device
+// functions); result[i] = the method's return value.
+int hk_debug(uint32_t *planes, int64_t n, int phase, int pid, int arg, int arg2, int difficulty, uint64_t seed,
+             uint32_t env_id_base, uint8_t *result, uint32_t *status)
+{
+    uint4 *st = reinterpret_cast<uint4 *>(planes);
+    Params p = make_params(1, difficulty, 500, 0, seed, env_id_base, nullptr, status);
+    for (int64_t i = 0; i < n; ++i) {
+        Env s;
+        uint16_t sb[kSlots] = {0};
+        load_env<1>(s, sb, st, n, i);
+        int res = 0;
+        switch (phase) {
+        case INV_PHASE_TRY_MOVE: res = pid ? try_move(s, 1, arg) : try_move(s, 0, arg); break;
+        case INV_PHASE_SPAWN_BULLET: res = pid ? spawn_bullet<1>(s, sb, 1, arg, status) : spawn_bullet<1>(s, sb, 0, arg, status); break;
+        case INV_PHASE_WIDE_SHOT: res = pid ? spawn_wide_shot<1>(s, sb, 1, arg, status) : spawn_wide_shot<1>(s, sb, 0, arg, status); break;
+        case INV_PHASE_RELOAD: reload_ammo(s); break;
+        case INV_PHASE_UPDATE_BULLETS: update_bullets<1>(s, sb); break;
+        case INV_PHASE_STEP_PLAYERS: step_players<1>(s, sb, arg, arg2, status); break;
+        case INV_PHASE_ENGINE_RESET: {
+            s.episode += 1u;
+            Draws dr;
+            dr.init(p, env_id_base + (uint32_t)i, s.episode, INV_STREAM_RESET, nullptr);
+            engine_reset(s, dr);
+            break;
+        }
+        case INV_PHASE_DUMMY_POLICY: {
+            Draws dr;
+            dr.init(p, env_id_base + (uint32_t)i, s.episode, s.step, nullptr);
+            res = dummy_policy(s, dr, difficulty);
+            break;
+        }
+        default: return -1;
+        }
+        result[i] = (uint8_t)res;
+        store_env<1>(s, sb, st, n, i);
+    }
+    return 0;
+}
+
+int hk_observation(const uint32_t *planes, int64_t n, int64_t i, int viewer, float *obs, float *extra)
+{
+    Env s;
+    uint16_t sb[kSlots] = {0};
+    load_env<1>(s, sb, reinterpret_cast<const uint4 *>(planes), n, i);
+    if (viewer == 0) emit(s, sb, 0, obs, extra, nullptr, nullptr);
+    else emit(s, sb, 0, nullptr, nullptr, obs, extra);
+    return 0;
+}
+
 } // extern "C"
 
 #ifdef HK_STANDALONE

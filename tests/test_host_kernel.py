@@ -46,3 +46,33 @@ def test_kernel_logic_under_address_and_ub_sanitizers(tmp_path):
                        env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
     assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-3000:]
     assert "sanitizer run ok" in r.stdout
+
+
+import reference_kat as K  # noqa: E402
+
+
+@pytest.mark.parametrize("name", K.ALL_KATS)
+def test_reference_unit_tests_through_the_kernel_logic_on_host(name):
+    """The reference's own unit tests (tests/reference_kat.py) against the product's engine
+    functions compiled for the host -- the CPU twin of tests/test_cuda_reference_kat.py."""
+    from engine_facade import HostKernelEngine
+    getattr(K, name)(lambda w, h: HostKernelEngine(w, h))
+
+
+FRESH = {
+    "host_hard": dict(mode="dummy", difficulty="hard", max_steps=500, n=512, T=600, seed=301, actions="uniform", draws="philox", resets="auto"),
+    "host_easy": dict(mode="dummy", difficulty="easy", max_steps=120, n=256, T=300, seed=302, actions="shooty", draws="philox", resets="auto"),
+    "host_selfplay": dict(mode="selfplay", difficulty="hard", max_steps=200, n=256, T=300, seed=303, actions="shooty", draws="philox", resets="auto"),
+    "host_table": dict(mode="dummy", difficulty="hard", max_steps=90, n=200, T=200, seed=305, actions="charge", draws="table", resets="manual"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FRESH))
+def test_kernel_logic_on_host_matches_oracle_on_fresh_seeds(name):
+    from backends import OracleBackend
+    sc = FRESH[name]
+    want = run_scenario(OracleBackend(sc, nthreads=4), sc, record_obs=(sc["n"] <= 256))
+    got = run_scenario(HostKernelBackend(sc), sc, record_obs=(sc["n"] <= 256))
+    compare(got, want, float_rtol=1e-6, what=name)
+    assert np.array_equal(got["reward_f32"], want["reward_f32"])
+    assert np.array_equal(got["episode_return"], want["episode_return"])
