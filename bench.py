@@ -51,6 +51,11 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg (0 = skip)")
     ap.add_argument("--cpu-sample-envs", type=int, default=65536)
     ap.add_argument("--sweep", action="store_true", help="also time 4K..4M envs (written to stderr)")
+    ap.add_argument("--ppo", type=int, default=1, help="1 = also run the PPO block (BASELINE.json configs[3]/[4]), 0 = skip")
+    ap.add_argument("--ppo-envs3", type=int, default=65536, help="envs per GPU of the selfplay PPO run (configs[3])")
+    ap.add_argument("--ppo-envs4", type=int, default=1 << 20, help="envs per GPU of the sharded vs_dummy PPO run (configs[4])")
+    ap.add_argument("--ppo-samples", type=int, default=1 << 21, help="samples per GPU per PPO iteration (rollout_steps = this / envs)")
+    ap.add_argument("--ppo-iters", type=int, default=3, help="PPO iterations per run (the first one is warm-up)")
     return ap.parse_args()
 
 
@@ -61,6 +66,81 @@ def measured_peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_tflops():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        return 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
+
+
+POLICY_FWD_FLOP = 92.6e6  # conv1..4 (3x3, 12-32-64-128-128 on 15x10) + the two 19204x256 heads, multiply-add = 2
+
+
+def ppo_block(args, rank, world, dev):
+    """PPO samples/s, the second half of BASELINE.json's metric, on its two policy-driven configs:
+    configs[3] selfplay (both players policy-driven, batched bf16 inference + fused step) and
+    configs[4] env-sharded vs_dummy/hard PPO with the NCCL gradient all-reduce. Both run the
+    reference's update schedule (4 epochs over every sample, ppo_agent.py:19-27 / :190-231) through
+    the repo's own trainer (inversus_b200.training.train). The rollout is cut to `--ppo-samples`
+    samples per GPU per iteration so the block fits the bench budget (the reference collects 128
+    steps per env, training.py:105-107; per-sample cost does not depend on that length) -- the
+    line states the rollout length used. One extra run with epochs=1 is labelled as such."""
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from inversus_b200.training import train
+
+    peak_tf, peak_src = measured_tflops()
+
+    def run(name, mode, envs_per_gpu, epochs, iters):
+        n_total = envs_per_gpu * world
+        T = max(2, args.ppo_samples // envs_per_gpu)
+        batch = 32768 if envs_per_gpu * T >= (1 << 19) else 16384
+        torch.manual_seed(args.seed)
+        with tempfile.TemporaryDirectory() as tmp:
+            out = train(mode, n_total, total_steps=n_total * T * iters, log_dir=tmp,
+                        opponent_difficulty="hard", precision="bf16", rollout_steps=T, batch_size=batch, epochs=epochs,
+                        seed=args.seed, quiet=True, save=False, time_allreduce=True)
+        st = out["steady_state"]
+        # every rank times its own iterations; collectives keep them in step, report the slowest
+        t = torch.tensor([st["rollout_s"], st["update_s"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        roll_s, upd_s = t.tolist()
+        n = st["samples"]  # whole-job samples in the timed iterations
+        infer_flop = POLICY_FWD_FLOP * n * (2 if mode == "selfplay" else 1)
+        infer_flop += POLICY_FWD_FLOP * n_total * st["iterations"]  # the bootstrap value pass after each rollout
+        upd_flop = 3 * POLICY_FWD_FLOP * n * epochs
+        r = {"run": name, "mode": mode, "envs_per_gpu": envs_per_gpu, "total_envs": n_total, "rollout_steps": T,
+             "epochs": epochs, "batch_size_per_gpu": batch, "iterations_timed": st["iterations"],
+             "samples_per_s": n / (roll_s + upd_s),
+             "rollout_env_steps_per_s": n / roll_s,
+             "update_samples_per_s": n * epochs / upd_s,
+             "rollout_s": roll_s, "update_s": upd_s,
+             "inference_tflops_per_gpu": infer_flop / roll_s / 1e12 / world,
+             "update_tflops_per_gpu": upd_flop / upd_s / 1e12 / world,
+             "inference_frac_of_bf16_sustained": infer_flop / roll_s / 1e12 / world / peak_tf,
+             "update_frac_of_bf16_sustained": upd_flop / upd_s / 1e12 / world / peak_tf,
+             "precision": "bf16", "packed_encoder": out.get("packed_encoder"), "cuda_graph_rollout": out.get("cuda_graph"),
+             "allreduce": out.get("allreduce"),
+             "policy_loss": out.get("policy_loss"), "value_loss": out.get("value_loss"), "entropy": out.get("entropy")}
+        return r
+
+    runs = [
+        run("configs[3] selfplay, reference schedule (4 epochs)", "selfplay", args.ppo_envs3, 4, args.ppo_iters),
+        run("configs[4] vs_dummy hard sharded, reference schedule (4 epochs)", "vs_dummy", args.ppo_envs4, 4, args.ppo_iters),
+        run("configs[4] vs_dummy hard sharded, epochs=1 (NOT the reference schedule)", "vs_dummy", args.ppo_envs4, 1,
+            args.ppo_iters),
+    ]
+    return {"metric": "ppo_samples_per_sec", "unit": "samples/s (whole job; rollout + update wall clock, max over ranks)",
+            "bf16_peak_tflops": peak_tf, "peak_source": peak_src, "policy_fwd_flop_per_sample": POLICY_FWD_FLOP,
+            "note": "update_samples_per_s counts every epoch's pass over a sample; TFLOP/s = 3 x fwd FLOPs per "
+                    "sample-pass for the update, fwd FLOPs per policy evaluation for the rollout (env step, sampling "
+                    "and rollout stores are inside rollout_s)",
+            "runs": runs}
 
 
 def recorded_traffic(obs_dtype, mode, n_envs):
@@ -336,6 +416,7 @@ def main():
     # ------------------------------------------------------------------ e2e: host buffers through inv_step_host
     e2e = None
     e2e_variants = None
+    esim = out = None
     if args.e2e_steps > 0:
         ne = args.e2e_envs or n
         esim = sim if ne == n else BatchedInversus(ne, args.mode, args.difficulty, args.max_episode_steps,
@@ -371,7 +452,8 @@ def main():
             elif nthreads == 0 or args.obs_dtype != "f32" or ne < 4096:
                 d2h = ne * (views * 1800 * elem + small)
             else:
-                d2h = ne * small + views * (ne * 256 + int(hp["dma_fraction"] * ne) * 7200)
+                n_dma = int(hp["dma_fraction"] * ne)  # envs whose fp32 observation crosses PCIe as is
+                d2h = ne * small + views * ((ne - n_dma) * 256 + n_dma * 7200)
             return {"value": ne * world * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": ne * views,
                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "envs_per_gpu": ne,
                     "ms_per_step": 1e3 * dt / args.e2e_steps, "host_threads": hp["threads"],
@@ -448,13 +530,23 @@ def main():
                          f"oracle/inversus_oracle.c, fp32 obs written every step, {r['cores']} pthreads",
                "python_loop": run_python_loop(args, seconds=min(4.0, args.cpu_seconds))}
 
+    # ------------------------------------------------------------------ PPO block (all ranks)
+    ppo = None
+    if args.ppo:
+        sim.close()
+        sim = esim = out = acts = acts2 = None  # device buffers and the pinned host buffers of the e2e leg
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        ppo = ppo_block(args, rank, world, dev)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(args, world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_variants": e2e_variants, "gpu_launches": launches,
-            "clocks": clk.summary(),
+            "clocks": clk.summary(), "ppo": ppo,
         }
         emit(line)
     if world > 1:

@@ -58,7 +58,10 @@ typedef enum {
 
 typedef enum { INV_MODE_DUMMY = 0, INV_MODE_SELFPLAY = 1 } inv_mode;         /* env_wrappers.py:305-316 */
 typedef enum { INV_DIFFICULTY_EASY = 0, INV_DIFFICULTY_HARD = 1 } inv_difficulty; /* env_wrappers.py:81-89 */
-typedef enum { INV_OBS_F32 = 0, INV_OBS_BF16 = 1, INV_OBS_U8 = 2 } inv_obs_dtype;
+/* INV_OBS_NONE: no observation tensor at all (the extra vector and every other output are still
+ * written). For consumers that read the packed state directly -- the PPO trainer's policy does,
+ * through inv_encode_fwd -- the step then moves about 200 bytes per env instead of 3.8-7.4 KB. */
+typedef enum { INV_OBS_F32 = 0, INV_OBS_BF16 = 1, INV_OBS_U8 = 2, INV_OBS_NONE = 3 } inv_obs_dtype;
 
 /* inv_config.flags */
 #define INV_FLAG_AUTO_RESET 1u /* fuse the trainer's reset-on-done (training.py:140-151) into step */
@@ -240,6 +243,25 @@ int inv_ln_relu_fwd(const void *x, const void *res, const void *cbias, const voi
 int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *cbias, const void *gamma,
                     const void *beta, const float *mean, const float *rstd, int64_t B, int32_t D, int32_t C,
                     void *dx, float *dgamma, float *dbeta, float *dcbias, float *partials, void *stream);
+
+/* Layer 1 of the policy evaluated straight from packed env states (csrc/encoder_kernels.cu):
+ *   y = relu(LayerNorm(conv1(build_observation(state)) + b1) * gamma + beta)
+ * i.e. inversus_rl/policies.py:27-31,94 applied to the observation of env_wrappers.py:173-245,
+ * without materialising the observation. packed_dev: [5, stride] uint4 planes (a copy or view of
+ * INV_BUF_PACKED_STATE), entries [0, count); view 0 = P1, 1 = P2. w1: [32,12,3,3] fp32 (checkpoint
+ * layout), b1: [32]; gamma_hwc / beta_hwc: LayerNorm affine permuted to [10,15,32] fp32.
+ *   fwd: y_out [count,10,15,32] bf16 (channels-last), extra_out [count,4] f32 (the extra vector of
+ *        env_wrappers.py:238-243; may be NULL), mean_out / rstd_out [count] f32 for the backward.
+ *   bwd: dy [count,10,15,32] bf16 -> dw1 [32,12,3,3], db1 [32], dgamma_hwc / dbeta_hwc [4800], fp32.
+ *        partials: scratch of inv_encode_partials_floats() floats. Deterministic (no atomics).
+ * Pure functions of their arguments: no handle; they run on the current device. */
+int inv_encode_partials_floats(void);
+int inv_encode_fwd(const void *packed_dev, int64_t stride, int64_t count, int view, const float *w1, const float *b1,
+                   const float *gamma_hwc, const float *beta_hwc, float eps, void *y_out, float *extra_out,
+                   float *mean_out, float *rstd_out, void *stream);
+int inv_encode_bwd(const void *packed_dev, int64_t stride, int64_t count, int view, const float *w1, const float *b1,
+                   const float *gamma_hwc, const float *beta_hwc, const float *mean, const float *rstd, const void *dy,
+                   float *dw1, float *db1, float *dgamma_hwc, float *dbeta_hwc, float *partials, void *stream);
 
 /* Per-row transpose + fp32<->bf16 conversion: dst[r][b*A + a] = src[r][a*B + b], a < A, b < B, for
  * `rows` rows with leading dimensions ld_src / ld_dst (elements). Exactly one side is fp32, the

@@ -8,13 +8,15 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libinversus_b200.so")
-SOURCES = [os.path.join(CSRC, "inversus_b200.cu"), os.path.join(CSRC, "policy_kernels.cu")]
+SOURCES = [os.path.join(CSRC, "inversus_b200.cu"), os.path.join(CSRC, "policy_kernels.cu"),
+           os.path.join(CSRC, "encoder_kernels.cu")]
 HOST_SOURCES = [os.path.join(CSRC, "host_expand.cpp")]  # plain C++ (AVX2 intrinsics), compiled by g++
 DEPS = SOURCES + HOST_SOURCES + [os.path.join(CSRC, "inversus_kernels.cuh"),
                   os.path.join(os.path.dirname(HERE), "include", "inversus_b200.h")]
 
+# --cudart=shared: the artefact links libcudart dynamically instead of embedding the whole runtime
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "--cudart=shared"]
 
 
 def find_nvcc() -> str:

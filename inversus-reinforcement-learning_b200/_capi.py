@@ -16,7 +16,7 @@ OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_INVALID_ACTION, ERR_BULLET_OVERFLOW, ERR_NOT_RESET, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
 MODE = {"dummy": 0, "selfplay": 1}
 DIFFICULTY = {"easy": 0, "hard": 1}
-OBS_DTYPE = {"f32": 0, "float32": 0, "bf16": 1, "bfloat16": 1, "u8": 2, "uint8": 2}
+OBS_DTYPE = {"f32": 0, "float32": 0, "bf16": 1, "bfloat16": 1, "u8": 2, "uint8": 2, "none": 3}
 FLAG_AUTO_RESET, FLAG_P2_VIEW = 1, 2
 (BUF_OBS_P1, BUF_EXTRA_P1, BUF_OBS_P2, BUF_EXTRA_P2, BUF_REWARD, BUF_DONE, BUF_INFO,
  BUF_EPISODE_STEPS, BUF_EPISODE_RETURN, BUF_PACKED_STATE, BUF_DEBUG_RESULT) = range(11)
@@ -77,6 +77,9 @@ SYMBOLS = {
     "inv_ln_relu_bwd": (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 6),
     "inv_transpose_cast": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_int64,
                                      C.c_int32, C.c_int32, C.c_void_p]),
+    "inv_encode_partials_floats": (C.c_int, []),
+    "inv_encode_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int] + [C.c_void_p] * 4 + [C.c_float] + [C.c_void_p] * 5),
+    "inv_encode_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int] + [C.c_void_p] * 13),
     "inv_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32,
                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
@@ -89,7 +92,8 @@ class InversusError(RuntimeError):
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    # INVERSUS_B200_LIB selects another build of the SAME library (kernel-shape experiments under profiles/)
+    return os.environ.get("INVERSUS_B200_LIB") or _build.LIB_PATH
 
 
 def load() -> C.CDLL:

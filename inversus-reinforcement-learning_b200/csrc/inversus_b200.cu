@@ -38,7 +38,11 @@ struct inv_sim {
     // staging for the *_host calls: pinned host + device copies of the action ids
     int8_t *h_a1, *h_a2, *d_a1, *d_a2;
     uint32_t *h_status;
-    cudaStream_t host_stream;
+    cudaStream_t host_stream, copy_stream; // *_host calls: kernels on host_stream, D2H copies on copy_stream
+    // ordering of the *_host calls after launches the caller enqueued on its own streams
+    cudaEvent_t ev_last;
+    bool ev_last_valid, need_device_sync;
+    cudaEvent_t ev_kernel[8], ev_bits[8], ev_t0, ev_t1;
     // the small per-env outputs live in ONE device block (extra1, extra2, reward, episode_steps,
     // episode_return, done, info) so that the *_host calls can fetch them with a single copy
     char *d_small, *h_small;
@@ -117,7 +121,8 @@ struct DeviceGuard {
     }
 };
 
-size_t obs_elem_bytes(int dt) { return dt == INV_OBS_F32 ? 4 : dt == INV_OBS_BF16 ? 2 : 1; }
+size_t obs_elem_bytes(int dt) { return dt == INV_OBS_F32 ? 4 : dt == INV_OBS_BF16 ? 2 : dt == INV_OBS_U8 ? 1 : 0; }
+size_t obs_env_bytes(int dt) { return (size_t)INV_OBS_ELEMS * obs_elem_bytes(dt); }
 
 Params base_params(const inv_sim *s)
 {
@@ -151,14 +156,20 @@ Params base_params(const inv_sim *s)
 // lock-step). The narrower the observation, the more logic per stored byte, so bf16/u8 step
 // kernels use more logic warps per CTA: E = 64 (bf16, one view) or 128 (bf16 two views, u8).
 constexpr int kTileEnvs = 32;
-constexpr size_t kSmallBlockMax = 4u << 20; // up to 4 MB of small outputs go through one staged copy
+// fp32 observations, large batches (round 2, profiles/r2_variants_f32*.txt): 32-byte stores plus
+// more store warps per CTA lift the step kernel from 6.39 to 6.93 TB/s (a pure store stream in
+// the same shape reaches 7.1-7.5 TB/s, profiles/r2_store_ceiling.txt). Small batches keep the
+// 32-env / 128-thread shape (more CTAs, shorter critical path).
+#ifndef INV_WIDE_MIN_ENVS
+#define INV_WIDE_MIN_ENVS 131072
+#endif
 
 template <int OP, int DT, bool P2V, bool INDEXED, int E, int T = kThreads>
 cudaError_t launch_one(const Params &p, int sm_count, cudaStream_t st)
 {
     (void)sm_count;
     auto kern = inv_kernel<OP, DT, P2V, INDEXED, E, T>;
-    constexpr size_t smem = smem_bytes<E, P2V, INDEXED>();
+    constexpr size_t smem = smem_bytes<E, P2V, INDEXED, DT>();
     static bool configured[64] = {}; // per instantiation and per device (function attributes are per device)
     int dev = 0;
     cudaGetDevice(&dev);
@@ -177,9 +188,18 @@ cudaError_t launch_one(const Params &p, int sm_count, cudaStream_t st)
 template <int OP, int DT, bool P2V, bool INDEXED>
 cudaError_t launch_e(const Params &p, int sm_count, cudaStream_t st)
 {
-    if constexpr (OP == OP_STEP && !INDEXED && DT != INV_OBS_F32) {
+    if constexpr (DT == INV_OBS_NONE && !INDEXED && OP != OP_DEBUG) {
+        return launch_one<OP, DT, P2V, false, 128, 128>(p, sm_count, st); // pure thread-per-env, no store phase
+    } else if constexpr (OP == OP_STEP && !INDEXED && DT != INV_OBS_F32) {
         constexpr int E = (DT == INV_OBS_BF16 && !P2V) ? 64 : 128;
         return launch_one<OP_STEP, DT, P2V, false, E>(p, sm_count, st);
+    } else if constexpr (DT == INV_OBS_F32 && !INDEXED && OP != OP_DEBUG) {
+        if (p.count >= INV_WIDE_MIN_ENVS) {
+            if constexpr (OP == OP_STEP && !P2V) return launch_one<OP, DT, P2V, false, 64, 256>(p, sm_count, st);
+            else if constexpr (OP == OP_STEP) return launch_one<OP, DT, P2V, false, 64, 384>(p, sm_count, st);
+            else return launch_one<OP, DT, P2V, false, 128, 512>(p, sm_count, st);
+        }
+        return launch_one<OP, DT, P2V, INDEXED, kTileEnvs>(p, sm_count, st);
     } else {
         return launch_one<OP, DT, P2V, INDEXED, kTileEnvs>(p, sm_count, st);
     }
@@ -196,6 +216,7 @@ cudaError_t launch(const Params &p, int dt, bool p2v, int sm_count, cudaStream_t
         INV_CASE(INV_OBS_F32)
         INV_CASE(INV_OBS_BF16)
         INV_CASE(INV_OBS_U8)
+        INV_CASE(INV_OBS_NONE)
     default:
         return cudaErrorInvalidValue;
     }
@@ -285,7 +306,7 @@ int inv_create(const inv_config *cfg, inv_sim **out)
         return fail(INV_ERR_INVALID_ARG, "Unknown opponent_type"); // env_wrappers.py:316
     if (cfg->difficulty != INV_DIFFICULTY_EASY && cfg->difficulty != INV_DIFFICULTY_HARD)
         return fail(INV_ERR_INVALID_ARG, "inv_create: difficulty must be easy(0) or hard(1)");
-    if (cfg->obs_dtype < INV_OBS_F32 || cfg->obs_dtype > INV_OBS_U8)
+    if (cfg->obs_dtype < INV_OBS_F32 || cfg->obs_dtype > INV_OBS_NONE)
         return fail(INV_ERR_INVALID_ARG, "inv_create: unknown obs_dtype");
     if (cfg->max_episode_steps <= 0) return fail(INV_ERR_INVALID_ARG, "inv_create: max_episode_steps must be positive");
     if (cfg->env_id_base < 0 || cfg->env_id_base + cfg->n_envs > 0xFFFFFFFFll)
@@ -322,8 +343,10 @@ int inv_create(const inv_config *cfg, inv_sim **out)
         }                                                                        \
     } while (0)
     ALLOC(s->state, (size_t)n * INV_PACKED_STATE_BYTES);
-    ALLOC(s->obs1, obs_bytes);
-    if (p2v) ALLOC(s->obs2, obs_bytes);
+    if (obs_bytes) {
+        ALLOC(s->obs1, obs_bytes);
+        if (p2v) ALLOC(s->obs2, obs_bytes);
+    }
     {
         auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
         size_t o = 0;
@@ -355,11 +378,15 @@ int inv_create(const inv_config *cfg, inv_sim **out)
     cudaMemset(s->status, 0, 4);
     cudaMemset(s->d_small, 0, s->small_bytes);
     cudaMemset(s->dbg, 0, (size_t)n);
-    if ((s->small_bytes <= kSmallBlockMax && cudaMallocHost((void **)&s->h_small, s->small_bytes) != cudaSuccess) ||
-        cudaMallocHost((void **)&s->h_a1, (size_t)n) != cudaSuccess ||
-        cudaMallocHost((void **)&s->h_a2, (size_t)n) != cudaSuccess ||
-        cudaMallocHost((void **)&s->h_status, 4) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s->host_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    bool ok = cudaMallocHost((void **)&s->h_status, 4) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&s->host_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&s->ev_last, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreate(&s->ev_t0) == cudaSuccess && cudaEventCreate(&s->ev_t1) == cudaSuccess;
+    for (int c = 0; ok && c < 8; ++c)
+        ok = cudaEventCreateWithFlags(&s->ev_kernel[c], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s->ev_bits[c], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
         fail(INV_ERR_CUDA, "pinned staging / stream allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         inv_destroy(s);
         return INV_ERR_CUDA;
@@ -386,6 +413,14 @@ int inv_destroy(inv_sim *s)
     if (s->h_a1) cudaFreeHost(s->h_a1);
     if (s->h_a2) cudaFreeHost(s->h_a2);
     if (s->h_status) cudaFreeHost(s->h_status);
+    if (s->ev_last) cudaEventDestroy(s->ev_last);
+    if (s->ev_t0) cudaEventDestroy(s->ev_t0);
+    if (s->ev_t1) cudaEventDestroy(s->ev_t1);
+    for (int c = 0; c < 8; ++c) {
+        if (s->ev_kernel[c]) cudaEventDestroy(s->ev_kernel[c]);
+        if (s->ev_bits[c]) cudaEventDestroy(s->ev_bits[c]);
+    }
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     for (int v = 0; v < 2; ++v) {
         if (s->d_bits[v]) cudaFree(s->d_bits[v]);
         if (s->h_bits[v]) cudaFreeHost(s->h_bits[v]);
@@ -402,6 +437,57 @@ int inv_get_config(const inv_sim *s, inv_config *out)
     return INV_OK;
 }
 
+// Launches enqueued on the caller's streams are remembered through one event, so that the
+// synchronous *_host calls (which run on the handle's own streams) can order themselves after them
+// without a device-wide synchronisation. A launch recorded into a CUDA graph cannot be tracked this
+// way; from then on the *_host calls fall back to cudaDeviceSynchronize.
+static void note_launch(inv_sim *s, cudaStream_t st)
+{
+    s->launches += 1;
+    if (st == s->host_stream) return;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone ||
+        cudaEventRecord(s->ev_last, st) != cudaSuccess) {
+        cudaGetLastError();
+        s->need_device_sync = true;
+        return;
+    }
+    s->ev_last_valid = true;
+}
+
+static int order_host_stream(inv_sim *s)
+{
+    if (s->need_device_sync) CUDA_TRY(cudaDeviceSynchronize());
+    else if (s->ev_last_valid) CUDA_TRY(cudaStreamWaitEvent(s->host_stream, s->ev_last, 0));
+    return INV_OK;
+}
+
+// The same launch restricted to envs [first, first + count): every per-env pointer moves, the plane
+// stride and the global-id base keep describing the whole handle.
+static Params chunk_params(const Params &b, int64_t first, int64_t count, size_t env_bytes)
+{
+    Params p = b;
+    p.state = b.state + first;
+    p.count = count;
+    if (b.a1) p.a1 = b.a1 + first;
+    if (b.a2) p.a2 = b.a2 + first;
+    if (b.table) p.table = b.table + first * INV_TABLE_STRIDE;
+    p.obs1 = static_cast<char *>(b.obs1) + (size_t)first * env_bytes;
+    if (b.obs2) p.obs2 = static_cast<char *>(b.obs2) + (size_t)first * env_bytes;
+    if (b.bits1) p.bits1 = b.bits1 + first * 16;
+    if (b.bits2) p.bits2 = b.bits2 + first * 16;
+    p.extra1 = b.extra1 + first * 4;
+    if (b.extra2) p.extra2 = b.extra2 + first * 4;
+    p.reward = b.reward + first;
+    p.done = b.done + first;
+    p.info = b.info + first;
+    p.dbg = b.dbg + first;
+    p.ep_steps = b.ep_steps + first;
+    p.ep_return = b.ep_return + first;
+    p.env_id_base = b.env_id_base + (uint32_t)first;
+    return p;
+}
+
 int inv_reset(inv_sim *s, void *stream)
 {
     if (!s) return fail(INV_ERR_INVALID_ARG, "inv_reset: null handle");
@@ -409,7 +495,7 @@ int inv_reset(inv_sim *s, void *stream)
     Params p = base_params(s);
     CUDA_TRY((launch<OP_RESET, false>(p, s->cfg.obs_dtype, (s->cfg.flags & INV_FLAG_P2_VIEW) != 0, s->sm_count,
                                       (cudaStream_t)stream)));
-    s->launches += 1;
+    note_launch(s, (cudaStream_t)stream);
     s->was_reset = true;
     return INV_OK;
 }
@@ -425,11 +511,13 @@ int inv_reset_envs(inv_sim *s, const int64_t *idx_dev, int64_t count, void *stre
     p.count = count;
     CUDA_TRY((launch<OP_RESET, true>(p, s->cfg.obs_dtype, (s->cfg.flags & INV_FLAG_P2_VIEW) != 0, s->sm_count,
                                      (cudaStream_t)stream)));
-    s->launches += 1;
+    note_launch(s, (cudaStream_t)stream);
     return INV_OK;
 }
 
-static int step_impl(inv_sim *s, const int8_t *a1, const int8_t *a2, void *stream, uint4 *bits1, uint4 *bits2)
+// One fused step launch over envs [first, first + count).
+static int step_impl(inv_sim *s, const int8_t *a1, const int8_t *a2, void *stream, uint4 *bits1, uint4 *bits2,
+                     int64_t first, int64_t count)
 {
     if (!s || !a1) return fail(INV_ERR_INVALID_ARG, "inv_step: null argument");
     if (!s->was_reset) return fail(INV_ERR_NOT_RESET, "inv_step before inv_reset");
@@ -441,63 +529,72 @@ static int step_impl(inv_sim *s, const int8_t *a1, const int8_t *a2, void *strea
     p.a2 = a2;
     p.bits1 = bits1;
     p.bits2 = bits2;
+    if (first != 0 || count != s->n) p = chunk_params(p, first, count, obs_env_bytes(s->cfg.obs_dtype));
     CUDA_TRY((launch<OP_STEP, false>(p, s->cfg.obs_dtype, (s->cfg.flags & INV_FLAG_P2_VIEW) != 0, s->sm_count,
                                      (cudaStream_t)stream)));
-    s->launches += 1;
+    note_launch(s, (cudaStream_t)stream);
     return INV_OK;
 }
 
 int inv_step(inv_sim *s, const int8_t *a1, const int8_t *a2, void *stream)
 {
-    return step_impl(s, a1, a2, stream, nullptr, nullptr);
+    return step_impl(s, a1, a2, stream, nullptr, nullptr, 0, s ? s->n : 0);
 }
 
-// After the stream has been synchronised: scatter the staged small-output block to the caller.
-static void scatter_small_outputs(inv_sim *s, float *extra_p1, float *extra_p2, float *reward, uint8_t *done,
-                                  uint8_t *info, int32_t *episode_steps, double *episode_return)
+// ------------------------------------------------------------------------------------------------
+// Host-buffer calls (the numpy contract of MultiEnvRunner.step). The batch is cut into up to 8 env
+// chunks; chunk c's kernel runs on host_stream while copy_stream brings chunk c-1's outputs to the
+// host, and the host threads expand the packed observation rows of chunk c-2.
+constexpr int kMaxHostChunks = 8;
+constexpr int64_t kHostChunkMinEnvs = 131072;  // chunks keep the wide launch shape
+constexpr size_t kStagedSmallMax = 8u << 20;   // small outputs: one staged copy up to 8 MB, direct copies above
+
+struct SmallOut {
+    float *extra_p1, *extra_p2, *reward;
+    uint8_t *done, *info;
+    int32_t *episode_steps;
+    double *episode_return;
+};
+
+static int ensure_host_staging(inv_sim *s)
 {
-    if (!s->h_small) return;
     const size_t n = (size_t)s->n;
-    if (extra_p1) memcpy(extra_p1, s->h_small + s->off_extra1, n * 16);
-    if (extra_p2 && s->extra2) memcpy(extra_p2, s->h_small + s->off_extra2, n * 16);
-    if (reward) memcpy(reward, s->h_small + s->off_reward, n * 4);
-    if (episode_steps) memcpy(episode_steps, s->h_small + s->off_steps, n * 4);
-    if (episode_return) memcpy(episode_return, s->h_small + s->off_return, n * 8);
-    if (done) memcpy(done, s->h_small + s->off_done, n);
-    if (info) memcpy(info, s->h_small + s->off_info, n);
-}
-
-static int copy_small_outputs(inv_sim *s, cudaStream_t st, float *extra_p1, float *extra_p2, float *reward,
-                              uint8_t *done, uint8_t *info, int32_t *episode_steps, double *episode_return)
-{
-    const int64_t n = s->n;
-    if (extra_p2 && !s->extra2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
-    if (s->h_small) { // small batches: one copy of the whole block, scattered on the host after the sync
-        CUDA_TRY(cudaMemcpyAsync(s->h_small, s->d_small, s->small_bytes, cudaMemcpyDeviceToHost, st));
-        return INV_OK;
-    }
-    if (extra_p1) CUDA_TRY(cudaMemcpyAsync(extra_p1, s->extra1, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-    if (extra_p2) {
-        if (!s->extra2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
-        CUDA_TRY(cudaMemcpyAsync(extra_p2, s->extra2, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-    }
-    if (reward) CUDA_TRY(cudaMemcpyAsync(reward, s->reward, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    if (done) CUDA_TRY(cudaMemcpyAsync(done, s->done, (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (info) CUDA_TRY(cudaMemcpyAsync(info, s->info, (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (episode_steps) CUDA_TRY(cudaMemcpyAsync(episode_steps, s->ep_steps, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    if (episode_return) CUDA_TRY(cudaMemcpyAsync(episode_return, s->ep_return, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    if (!s->h_a1) CUDA_TRY(cudaMallocHost((void **)&s->h_a1, n));
+    if (!s->h_a2) CUDA_TRY(cudaMallocHost((void **)&s->h_a2, n));
+    if (!s->h_small && s->small_bytes <= kStagedSmallMax) CUDA_TRY(cudaMallocHost((void **)&s->h_small, s->small_bytes));
     return INV_OK;
 }
 
-// Whole-observation copy straight from the device buffers (any dtype).
-static int copy_obs_plain(inv_sim *s, cudaStream_t st, void *obs_p1, void *obs_p2)
+// After the copies have landed: scatter the staged small-output block to the caller.
+static void scatter_small_outputs(inv_sim *s, const SmallOut &o)
 {
-    const size_t ob = (size_t)s->n * INV_OBS_ELEMS * obs_elem_bytes(s->cfg.obs_dtype);
-    if (obs_p1) CUDA_TRY(cudaMemcpyAsync(obs_p1, s->obs1, ob, cudaMemcpyDeviceToHost, st));
-    if (obs_p2) {
-        if (!s->obs2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
-        CUDA_TRY(cudaMemcpyAsync(obs_p2, s->obs2, ob, cudaMemcpyDeviceToHost, st));
+    if (!s->h_small) return;
+    const size_t n = (size_t)s->n;
+    if (o.extra_p1) memcpy(o.extra_p1, s->h_small + s->off_extra1, n * 16);
+    if (o.extra_p2 && s->extra2) memcpy(o.extra_p2, s->h_small + s->off_extra2, n * 16);
+    if (o.reward) memcpy(o.reward, s->h_small + s->off_reward, n * 4);
+    if (o.episode_steps) memcpy(o.episode_steps, s->h_small + s->off_steps, n * 4);
+    if (o.episode_return) memcpy(o.episode_return, s->h_small + s->off_return, n * 8);
+    if (o.done) memcpy(o.done, s->h_small + s->off_done, n);
+    if (o.info) memcpy(o.info, s->h_small + s->off_info, n);
+}
+
+// Small outputs of envs [first, first + count) to the host: the whole block into the staging buffer
+// (small batches, one copy), or straight into the caller's arrays.
+static int copy_small_outputs(inv_sim *s, cudaStream_t st, const SmallOut &o, int64_t first, int64_t count)
+{
+    if (s->h_small) {
+        if (first == 0) CUDA_TRY(cudaMemcpyAsync(s->h_small, s->d_small, s->small_bytes, cudaMemcpyDeviceToHost, st));
+        return INV_OK;
     }
+    const size_t f = (size_t)first, c = (size_t)count;
+    if (o.extra_p1) CUDA_TRY(cudaMemcpyAsync(o.extra_p1 + f * 4, s->extra1 + f * 4, c * 16, cudaMemcpyDeviceToHost, st));
+    if (o.extra_p2) CUDA_TRY(cudaMemcpyAsync(o.extra_p2 + f * 4, s->extra2 + f * 4, c * 16, cudaMemcpyDeviceToHost, st));
+    if (o.reward) CUDA_TRY(cudaMemcpyAsync(o.reward + f, s->reward + f, c * 4, cudaMemcpyDeviceToHost, st));
+    if (o.done) CUDA_TRY(cudaMemcpyAsync(o.done + f, s->done + f, c, cudaMemcpyDeviceToHost, st));
+    if (o.info) CUDA_TRY(cudaMemcpyAsync(o.info + f, s->info + f, c, cudaMemcpyDeviceToHost, st));
+    if (o.episode_steps) CUDA_TRY(cudaMemcpyAsync(o.episode_steps + f, s->ep_steps + f, c * 4, cudaMemcpyDeviceToHost, st));
+    if (o.episode_return) CUDA_TRY(cudaMemcpyAsync(o.episode_return + f, s->ep_return + f, c * 8, cudaMemcpyDeviceToHost, st));
     return INV_OK;
 }
 
@@ -515,46 +612,6 @@ static int ensure_bits_staging(inv_sim *s, bool p2)
     return INV_OK;
 }
 
-// f32 observations to host memory, faster than PCIe alone: the packed rows (256 B/env) cross PCIe
-// first; then the copy engine moves the f32 data of envs [0, nA) while the host threads expand the
-// packed rows of envs [nA, n) with non-temporal stores. nA follows the measured rates of the two.
-static int copy_obs_expand(inv_sim *s, cudaStream_t st, void *obs_p1, void *obs_p2)
-{
-    const int64_t n = s->n;
-    void *dst[2] = {obs_p1, obs_p2};
-    const void *src[2] = {s->obs1, s->obs2};
-    for (int v = 0; v < 2; ++v)
-        if (dst[v]) CUDA_TRY(cudaMemcpyAsync(s->h_bits[v], s->d_bits[v], (size_t)n * 256, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st)); // small outputs + packed rows have landed
-    const int64_t nA = (int64_t)((double)n * s->dma_frac) & ~(int64_t)255;
-    using clk = std::chrono::steady_clock;
-    const auto t0 = clk::now();
-    double expand_s = 0.0;
-    std::thread ex([&] {
-        for (int v = 0; v < 2; ++v)
-            if (dst[v]) inv_host::expand_f32(s->h_bits[v], static_cast<float *>(dst[v]), nA, n, s->host_threads);
-        expand_s = std::chrono::duration<double>(clk::now() - t0).count();
-    });
-    cudaError_t ce = cudaSuccess;
-    if (nA > 0)
-        for (int v = 0; v < 2 && ce == cudaSuccess; ++v)
-            if (dst[v]) ce = cudaMemcpyAsync(dst[v], src[v], (size_t)nA * INV_OBS_ELEMS * 4, cudaMemcpyDeviceToHost, st);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-    const double dma_s = std::chrono::duration<double>(clk::now() - t0).count();
-    ex.join();
-    if (ce != cudaSuccess) return fail(INV_ERR_CUDA, "observation copy: %s", cudaGetErrorString(ce));
-    s->last_dma_s = dma_s;
-    s->last_expand_s = expand_s;
-    if (s->dma_frac_auto && expand_s > 0.0) { // balance the two legs from their measured rates
-        const double r_exp = (double)(n - nA) / expand_s;
-        const double r_dma = nA > 0 && dma_s > 0.0 ? (double)nA / dma_s : r_exp * 0.5;
-        double f = r_dma / (r_dma + r_exp);
-        f = f < 0.0 ? 0.0 : (f > 0.9 ? 0.9 : f);
-        s->dma_frac = 0.5 * s->dma_frac + 0.5 * f;
-    }
-    return INV_OK;
-}
-
 int inv_step_host(inv_sim *s, const int8_t *a1, const int8_t *a2, void *obs_p1, float *extra_p1, void *obs_p2,
                   float *extra_p2, float *reward, uint8_t *done, uint8_t *info, int32_t *episode_steps,
                   double *episode_return)
@@ -563,45 +620,114 @@ int inv_step_host(inv_sim *s, const int8_t *a1, const int8_t *a2, void *obs_p1, 
     if (!s->was_reset) return fail(INV_ERR_NOT_RESET, "inv_step_host before inv_reset");
     const bool selfplay = s->cfg.mode == INV_MODE_SELFPLAY;
     if (selfplay && !a2) return fail(INV_ERR_INVALID_ARG, "opponent_policy required for selfplay mode");
+    if (obs_p1 && !s->obs1) return fail(INV_ERR_INVALID_ARG, "this handle keeps no observation tensor (INV_OBS_NONE)");
     if (obs_p2 && !s->obs2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
+    if (extra_p2 && !s->extra2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
     const int64_t n = s->n;
-    // discrete_to_action raises before anything is stepped (env_wrappers.py:302, :66)
-    for (int64_t i = 0; i < n; ++i) {
-        if ((uint8_t)a1[i] > 12) return fail(INV_ERR_INVALID_ACTION, "Invalid action_id: must be 0-12");
-        if (selfplay && (uint8_t)a2[i] > 12) return fail(INV_ERR_INVALID_ACTION, "Invalid action_id: must be 0-12");
+    // discrete_to_action raises before anything is stepped (env_wrappers.py:302, :66); one
+    // branch-free pass over the ids (vectorised by the compiler), then report
+    {
+        unsigned bad = 0;
+        for (int64_t i = 0; i < n; ++i) bad |= (unsigned)((uint8_t)a1[i] > 12);
+        if (selfplay)
+            for (int64_t i = 0; i < n; ++i) bad |= (unsigned)((uint8_t)a2[i] > 12);
+        if (bad) return fail(INV_ERR_INVALID_ACTION, "Invalid action_id: must be 0-12");
     }
     DeviceGuard g(s->cfg.device);
-    cudaStream_t st = s->host_stream;
-    // the *_host calls are synchronous: order them after whatever the caller enqueued on other
-    // streams for this handle (inv_step / inv_reset_envs on a torch stream, say)
-    CUDA_TRY(cudaDeviceSynchronize());
+    int rc = ensure_host_staging(s);
+    if (rc != INV_OK) return rc;
+    const bool expand = use_host_expand(s, obs_p1, obs_p2);
+    if (expand && (rc = ensure_bits_staging(s, obs_p2 != nullptr)) != INV_OK) return rc;
+    cudaStream_t ks = s->host_stream, cs = s->copy_stream;
+    if ((rc = order_host_stream(s)) != INV_OK) return rc;
+
     // action ids travel host -> pinned staging -> device on the handle's own stream
     memcpy(s->h_a1, a1, (size_t)n);
-    CUDA_TRY(cudaMemcpyAsync(s->d_a1, s->h_a1, (size_t)n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->d_a1, s->h_a1, (size_t)n, cudaMemcpyHostToDevice, ks));
     if (selfplay) {
         memcpy(s->h_a2, a2, (size_t)n);
-        CUDA_TRY(cudaMemcpyAsync(s->d_a2, s->h_a2, (size_t)n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s->d_a2, s->h_a2, (size_t)n, cudaMemcpyHostToDevice, ks));
     }
-    const bool expand = use_host_expand(s, obs_p1, obs_p2);
-    if (expand) {
-        int rc = ensure_bits_staging(s, obs_p2 != nullptr);
+
+    int nchunks = (int)(n / kHostChunkMinEnvs);
+    nchunks = nchunks < 1 ? 1 : (nchunks > kMaxHostChunks ? kMaxHostChunks : nchunks);
+    if (!(obs_p1 || obs_p2) && nchunks > 4) nchunks = 4; // small outputs only: fewer, larger copies
+    if (const char *e = getenv("INV_HOST_CHUNKS")) { // experiments (profiles/)
+        const int v = atoi(e);
+        if (v >= 1 && v <= kMaxHostChunks && (int64_t)v <= n / 256) nchunks = v;
+    }
+    if (s->h_small) nchunks = 1;
+    const int64_t per = ((n + nchunks - 1) / nchunks + 255) & ~(int64_t)255;
+    const SmallOut so = {extra_p1, extra_p2, reward, done, info, episode_steps, episode_return};
+    const size_t env_bytes = (size_t)INV_OBS_ELEMS * obs_elem_bytes(s->cfg.obs_dtype);
+    void *dst[2] = {obs_p1, obs_p2};
+    const void *src[2] = {s->obs1, s->obs2};
+    const double frac = expand ? s->dma_frac : 1.0; // share of each chunk's envs whose f32 data is copied directly
+    int64_t lo[kMaxHostChunks], mid[kMaxHostChunks], hi[kMaxHostChunks];
+
+    // all kernels are enqueued first (the launch stream never waits for the host to issue copies) ...
+    int used = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t first = (int64_t)c * per;
+        if (first >= n) break;
+        const int64_t count = (first + per <= n) ? per : n - first;
+        lo[c] = first;
+        hi[c] = first + count;
+        mid[c] = expand ? first + ((int64_t)((double)count * frac) & ~(int64_t)255) : first + count;
+        rc = step_impl(s, s->d_a1, selfplay ? s->d_a2 : nullptr, ks, expand ? s->d_bits[0] : nullptr,
+                       expand && obs_p2 ? s->d_bits[1] : nullptr, first, count);
         if (rc != INV_OK) return rc;
+        CUDA_TRY(cudaEventRecord(s->ev_kernel[c], ks));
+        used = c + 1;
     }
-    int rc = step_impl(s, s->d_a1, selfplay ? s->d_a2 : nullptr, st, expand ? s->d_bits[0] : nullptr,
-                       expand && obs_p2 ? s->d_bits[1] : nullptr);
-    if (rc != INV_OK) return rc;
-    rc = copy_small_outputs(s, st, extra_p1, extra_p2, reward, done, info, episode_steps, episode_return);
-    if (rc != INV_OK) return rc;
+    // ... then the copy stream follows chunk by chunk
+    CUDA_TRY(cudaEventRecord(s->ev_t0, cs));
+    for (int c = 0; c < used; ++c) {
+        CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_kernel[c], 0));
+        if ((rc = copy_small_outputs(s, cs, so, lo[c], hi[c] - lo[c])) != INV_OK) return rc;
+        if (expand) { // packed rows of the envs the host will expand
+            for (int v = 0; v < 2; ++v)
+                if (dst[v] && hi[c] > mid[c])
+                    CUDA_TRY(cudaMemcpyAsync(s->h_bits[v] + (size_t)mid[c] * 64, s->d_bits[v] + (size_t)mid[c] * 16,
+                                             (size_t)(hi[c] - mid[c]) * 256, cudaMemcpyDeviceToHost, cs));
+            CUDA_TRY(cudaEventRecord(s->ev_bits[c], cs));
+        }
+        for (int v = 0; v < 2; ++v) // the directly copied observations
+            if (dst[v] && mid[c] > lo[c])
+                CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(dst[v]) + (size_t)lo[c] * env_bytes,
+                                         static_cast<const char *>(src[v]) + (size_t)lo[c] * env_bytes,
+                                         (size_t)(mid[c] - lo[c]) * env_bytes, cudaMemcpyDeviceToHost, cs));
+    }
+    CUDA_TRY(cudaEventRecord(s->ev_t1, cs));
+
+    double expand_s = 0.0;
+    if (expand) { // host side: expand chunk c as soon as its packed rows have landed
+        using clk = std::chrono::steady_clock;
+        for (int c = 0; c < used; ++c) {
+            CUDA_TRY(cudaEventSynchronize(s->ev_bits[c]));
+            const auto t0 = clk::now();
+            for (int v = 0; v < 2; ++v)
+                if (dst[v] && hi[c] > mid[c])
+                    inv_host::expand_f32(s->h_bits[v], static_cast<float *>(dst[v]), mid[c], hi[c], s->host_threads);
+            expand_s += std::chrono::duration<double>(clk::now() - t0).count();
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    scatter_small_outputs(s, so);
     if (expand) {
-        // d_bits[0] is always written by the kernel in this mode; only requested views are shipped
-        rc = copy_obs_expand(s, st, obs_p1, obs_p2); // synchronises the stream
-    } else {
-        rc = copy_obs_plain(s, st, obs_p1, obs_p2);
-        if (rc != INV_OK) return rc;
-        CUDA_TRY(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1);
+        const double dma_s = ms * 1e-3;
+        s->last_dma_s = dma_s;
+        s->last_expand_s = expand_s;
+        if (s->dma_frac_auto && expand_s > 0.0 && dma_s > 0.0) { // balance the two legs from their measured rates
+            const double r_exp = (1.0 - frac) / expand_s;
+            const double r_dma = frac > 0.0 ? frac / dma_s : r_exp * 0.5;
+            double f = r_dma / (r_dma + r_exp);
+            f = f < 0.0 ? 0.0 : (f > 0.9 ? 0.9 : f);
+            s->dma_frac = 0.5 * s->dma_frac + 0.5 * f;
+        }
     }
-    if (rc != INV_OK) return rc;
-    scatter_small_outputs(s, extra_p1, extra_p2, reward, done, info, episode_steps, episode_return);
     return INV_OK;
 }
 
@@ -627,18 +753,22 @@ int inv_get_host_path(const inv_sim *s, int *nthreads, double *dma_fraction, dou
 int inv_reset_host(inv_sim *s, void *obs_p1, float *extra_p1, void *obs_p2, float *extra_p2)
 {
     if (!s) return fail(INV_ERR_INVALID_ARG, "inv_reset_host: null handle");
+    if (obs_p1 && !s->obs1) return fail(INV_ERR_INVALID_ARG, "this handle keeps no observation tensor (INV_OBS_NONE)");
     if (obs_p2 && !s->obs2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
+    if (extra_p2 && !s->extra2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
     DeviceGuard g(s->cfg.device);
+    int rc = ensure_host_staging(s);
+    if (rc != INV_OK) return rc;
     cudaStream_t st = s->host_stream;
-    CUDA_TRY(cudaDeviceSynchronize()); // see inv_step_host
-    int rc = inv_reset(s, st);
-    if (rc != INV_OK) return rc;
-    rc = copy_small_outputs(s, st, extra_p1, extra_p2, nullptr, nullptr, nullptr, nullptr, nullptr);
-    if (rc != INV_OK) return rc;
-    rc = copy_obs_plain(s, st, obs_p1, obs_p2);
-    if (rc != INV_OK) return rc;
+    if ((rc = order_host_stream(s)) != INV_OK) return rc;
+    if ((rc = inv_reset(s, st)) != INV_OK) return rc;
+    const SmallOut so = {extra_p1, extra_p2, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if ((rc = copy_small_outputs(s, st, so, 0, s->n)) != INV_OK) return rc;
+    const size_t ob = (size_t)s->n * INV_OBS_ELEMS * obs_elem_bytes(s->cfg.obs_dtype);
+    if (obs_p1) CUDA_TRY(cudaMemcpyAsync(obs_p1, s->obs1, ob, cudaMemcpyDeviceToHost, st));
+    if (obs_p2) CUDA_TRY(cudaMemcpyAsync(obs_p2, s->obs2, ob, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    scatter_small_outputs(s, extra_p1, extra_p2, nullptr, nullptr, nullptr, nullptr, nullptr);
+    scatter_small_outputs(s, so);
     return INV_OK;
 }
 
@@ -760,7 +890,7 @@ int inv_obs_from_packed(inv_sim *s, const void *packed_dev, int64_t stride, int6
     default: return fail(INV_ERR_INVALID_ARG, "inv_obs_from_packed: unknown obs_dtype");
     }
     CUDA_TRY(ce);
-    s->launches += 1;
+    note_launch(s, (cudaStream_t)stream);
     return INV_OK;
 }
 
@@ -776,7 +906,7 @@ int inv_debug_phase(inv_sim *s, int phase, int pid, int arg, int arg2, void *str
     Params p = base_params(s);
     p.phase = phase; p.pid = pid; p.arg = arg; p.arg2 = arg2;
     CUDA_TRY((launch_one<OP_DEBUG, INV_OBS_F32, false, false, 32>(p, s->sm_count, (cudaStream_t)stream)));
-    s->launches += 1;
+    note_launch(s, (cudaStream_t)stream);
     return INV_OK;
 }
 

@@ -586,6 +586,25 @@ __device__ __forceinline__ StepResult rl_step(Env &s, uint16_t *sb, int a1, int 
 #ifndef INV_HOST_BUILD
 // ---- observation formats: how many store chunks per env and how a chunk is expanded ----
 template <int DT> struct ObsFmt;
+struct __align__(32) uint8v { uint4 lo, hi; }; // one 32-byte store (st.global.v8.b32, sm_100)
+#ifndef INV_F32_STORE32
+#define INV_F32_STORE32 1 // 32-byte stores: +5 % on the fp32 step kernel (profiles/r2_variants_f32.txt)
+#endif
+#if INV_F32_STORE32
+template <> struct ObsFmt<INV_OBS_F32> {  // 1800 f32 = 225 x 32 B, 8 bits per chunk
+    static constexpr int kChunks = 225, kBits = 8;
+    typedef uint8v chunk_t;
+    static __device__ __forceinline__ chunk_t expand(uint32_t b)
+    {
+        chunk_t c;
+        c.lo = make_uint4((b & 1u) ? 0x3F800000u : 0u, (b & 2u) ? 0x3F800000u : 0u,
+                          (b & 4u) ? 0x3F800000u : 0u, (b & 8u) ? 0x3F800000u : 0u);
+        c.hi = make_uint4((b & 16u) ? 0x3F800000u : 0u, (b & 32u) ? 0x3F800000u : 0u,
+                          (b & 64u) ? 0x3F800000u : 0u, (b & 128u) ? 0x3F800000u : 0u);
+        return c;
+    }
+};
+#else
 template <> struct ObsFmt<INV_OBS_F32> {  // 1800 f32 = 450 x 16 B, 4 bits per chunk
     static constexpr int kChunks = 450, kBits = 4;
     typedef uint4 chunk_t;
@@ -595,6 +614,7 @@ template <> struct ObsFmt<INV_OBS_F32> {  // 1800 f32 = 450 x 16 B, 4 bits per c
                           (b & 4u) ? 0x3F800000u : 0u, (b & 8u) ? 0x3F800000u : 0u);
     }
 };
+#endif
 template <> struct ObsFmt<INV_OBS_BF16> { // 1800 bf16 = 225 x 16 B, 8 bits per chunk
     static constexpr int kChunks = 225, kBits = 8;
     typedef uint4 chunk_t;
@@ -616,13 +636,33 @@ template <> struct ObsFmt<INV_OBS_U8> {   // 1800 u8 = 225 x 8 B, 8 bits per chu
     }
 };
 
+#ifndef INV_ST_PLAIN
+#define INV_ST_PLAIN 0
+#endif
+#if INV_ST_PLAIN
+__device__ __forceinline__ void st_stream(uint4 *p, uint4 v) { *p = v; }
+__device__ __forceinline__ void st_stream(uint2 *p, uint2 v) { *p = v; }
+#else
 __device__ __forceinline__ void st_stream(uint4 *p, uint4 v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(uint2 *p, uint2 v) { __stcs(p, v); }
+#endif
+template <> struct ObsFmt<INV_OBS_NONE> { // no observation tensor: the store phase is compiled out
+    static constexpr int kChunks = 1, kBits = 0; // never used: the kernel leaves before phase 2
+    typedef uint4 chunk_t;
+    static __device__ __forceinline__ chunk_t expand(uint32_t) { return make_uint4(0u, 0u, 0u, 0u); }
+};
+__device__ __forceinline__ void st_stream(uint8v *p, uint8v v)
+{
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.lo.x), "r"(v.lo.y), "r"(v.lo.z),
+                 "r"(v.lo.w), "r"(v.hi.x), "r"(v.hi.y), "r"(v.hi.z), "r"(v.hi.w)
+                 : "memory");
+}
 
-template <int E, bool P2V, bool INDEXED>
+template <int E, bool P2V, bool INDEXED, int DT = INV_OBS_F32>
 constexpr size_t smem_bytes()
 {
-    return (size_t)E * kRowWords * 4 * (P2V ? 2 : 1) + (size_t)kSlots * E * 2 + (INDEXED ? (size_t)E * 8 : 0);
+    return (DT == INV_OBS_NONE ? 0 : (size_t)E * kRowWords * 4 * (P2V ? 2 : 1)) + (size_t)kSlots * E * 2 +
+           (INDEXED ? (size_t)E * 8 : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -631,9 +671,10 @@ __global__ void __launch_bounds__(T) inv_kernel(const Params p)
 {
     static_assert(E <= T && E % 32 == 0 && T % 32 == 0, "tile must be whole warps");
     extern __shared__ __align__(16) uint32_t smem[];
+    constexpr bool kObs = DT != INV_OBS_NONE;
     uint32_t *rows1 = smem;
-    uint32_t *rows2 = rows1 + (P2V ? E * kRowWords : 0);
-    uint16_t *sbul = reinterpret_cast<uint16_t *>(rows2 + E * kRowWords);
+    uint32_t *rows2 = rows1 + (P2V && kObs ? E * kRowWords : 0);
+    uint16_t *sbul = reinterpret_cast<uint16_t *>(rows2 + (kObs ? E * kRowWords : 0));
     int64_t *s_env = reinterpret_cast<int64_t *>(sbul + kSlots * E); // INDEXED only
     typedef ObsFmt<DT> Fmt;
     typedef typename Fmt::chunk_t chunk_t;
@@ -713,19 +754,19 @@ __global__ void __launch_bounds__(T) inv_kernel(const Params p)
                 // extra vector: one coalesced 16 B store per env
                 const int64_t eo = (OP == OP_OBS) ? base + tid : ei;
                 if (OP == OP_OBS && p.view) { // viewer stays a compile-time constant in both arms
-                    build_row<E>(row1, s, sb, 1);
+                    if (kObs) build_row<E>(row1, s, sb, 1);
                     reinterpret_cast<float4 *>(p.extra1)[eo] = extra_vec(s, 1);
                 } else {
-                    build_row<E>(row1, s, sb, 0);
+                    if (kObs) build_row<E>(row1, s, sb, 0);
                     reinterpret_cast<float4 *>(p.extra1)[eo] = extra_vec(s, 0);
                 }
                 if (P2V) {
-                    build_row<E>(rows2 + tid * kRowWords, s, sb, 1);
+                    if (kObs) build_row<E>(rows2 + tid * kRowWords, s, sb, 1);
                     reinterpret_cast<float4 *>(p.extra2)[eo] = extra_vec(s, 1);
                 }
             }
         }
-        if (OP == OP_DEBUG) continue;
+        if (OP == OP_DEBUG || !kObs) continue;
         __syncthreads();
 
         // ------------------------------------------------------------ phase 2: streaming obs store

@@ -9,13 +9,19 @@
 //
 // Layout: a sample is D = H*W*C contiguous bf16 values in HWC order (the memory of a
 // channels-last tensor); gamma/beta are [D] bf16 in the same order. Statistics and all arithmetic
-// are fp32. Both kernels are persistent: a CTA keeps its slice of gamma/beta in registers and
-// walks over samples, so the affine parameters are read once per CTA instead of once per sample.
-// The backward keeps per-CTA dgamma/dbeta accumulators in shared memory (2*D floats, up to 150 KB)
-// and writes them as partials that a second small kernel reduces -- deterministic, no atomics.
+// are fp32. Both kernels are persistent. The forward walks over samples with one CTA per sample.
+// The backward (round 2) splits the FEATURE dimension over a thread-block cluster: each of the
+// 2/4/8 CTAs of a cluster owns D/CS columns, one 8-column vector per thread, so gamma/beta and the
+// dgamma/dbeta/dbias accumulators of those columns live in registers for the whole kernel (the
+// round-1 kernel kept 2*D floats per CTA in shared memory, which pinned it at one CTA per SM and
+// 0.24-0.41 of the HBM peak). The two per-sample row sums of the LayerNorm backward are combined
+// across the cluster through distributed shared memory, two samples per cluster barrier. Partials
+// are written per cluster and reduced by a second small kernel -- deterministic, no atomics.
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/inversus_b200.h"
 
@@ -302,6 +308,243 @@ __global__ void reduce_partials_kernel(const float *__restrict__ partials, int n
     else if (dcbias) dcbias[i - 2 * D] = s;
 }
 
+// ---- distributed-shared-memory helpers (raw PTX: the cooperative-groups cluster.sync() compiles
+// to MEMBAR.ALL.GPU + an L1 invalidate, far too heavy to sit in a streaming loop) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// a 4-byte store into a peer CTA's shared memory that completes `bytes` on the peer's mbarrier
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "f"(v), "r"(remote_bar)
+                 : "memory");
+}
+// spin until the barrier's phase with the given parity has completed; traps instead of hanging
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (spins > (1u << 26)) __trap(); // a protocol error must surface as a CUDA error, never as a hung GPU
+    }
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Clustered backward. Grid = nclusters * CS CTAs of kBwdThreads threads; cluster c walks over sample
+// groups c, c + nclusters, ... of S samples each. Thread `slot = rank * kBwdThreads + tid` owns
+// columns [8*slot, 8*slot + 8) of every sample.
+// partials layout (floats): [nclusters][2][D] (dgamma, dbeta) followed by [grid][C] (d conv bias).
+constexpr int kBwdThreads = 320;
+constexpr int kMaxCluster = 8;
+
+template <int S, bool HAS_RES>
+__global__ void __launch_bounds__(kBwdThreads, 2)
+ln_relu_bwd_cluster_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x, const uint4 *__restrict__ res,
+                           const uint4 *__restrict__ cbias, int cvecs, const uint4 *__restrict__ gamma,
+                           const uint4 *__restrict__ beta, const float *__restrict__ mean_in,
+                           const float *__restrict__ rstd_in, int64_t B, int nvec, uint4 *__restrict__ dx,
+                           float *__restrict__ partials)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    __shared__ __align__(8) uint64_t s_bar[2]; // one mbarrier per parity: counts the peers' row-sum bytes
+    const int nclusters = gridDim.x / cs, cid = blockIdx.x / cs;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int slot = rank * kBwdThreads + tid;
+    const bool active = slot < nvec;
+    const int D = nvec * 8;
+    const float inv_d = 1.0f / (float)D;
+
+    __shared__ float s_peer[2][kMaxCluster][2 * S]; // [parity][source rank][row sums], written by the peers
+    __shared__ float s_warp[kBwdThreads / 32][2 * S];
+    __shared__ float s_cb[kBwdThreads * 8];
+
+    // gamma, beta and the conv bias of this thread's 8 columns stay packed (4 registers each) and are
+    // unpacked where used: 96 registers per thread is what lets two CTAs share an SM
+    const uint4 gv = active ? gamma[slot] : make_uint4(0u, 0u, 0u, 0u);
+    const uint4 bv = active ? beta[slot] : make_uint4(0u, 0u, 0u, 0u);
+    // kBwdThreads % cvecs == 0, so slot % cvecs == tid % cvecs
+    const uint4 cbv = cbias ? cbias[tid % cvecs] : make_uint4(0u, 0u, 0u, 0u);
+    float dg[8], db[8], dcb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dg[j] = db[j] = dcb[j] = 0.f;
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&s_bar[0]), 1);
+        mbar_init(smem_u32(&s_bar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all(); // every CTA's barriers exist before any peer signals them
+    const uint32_t tx_bytes = (uint32_t)(2 * S * cs * sizeof(float));
+
+    const int64_t groups = (B + S - 1) / S;
+    int parity = 0;
+    uint32_t it = 0;
+    for (int64_t grp = cid; grp < groups; grp += nclusters, parity ^= 1, ++it) {
+        uint4 xv[S], dv[S], rv[HAS_RES ? S : 1];
+        float rs[S], nmr[S];
+#pragma unroll
+        for (int k = 0; k < S; ++k) { // all global loads of the group first
+            const int64_t smp = grp * S + k;
+            if (smp < B) {
+                rs[k] = rstd_in[smp];
+                nmr[k] = -mean_in[smp] * rs[k];
+                if (active) {
+                    xv[k] = x[smp * nvec + slot];
+                    dv[k] = dy[smp * nvec + slot];
+                    if (HAS_RES) rv[k] = res[smp * nvec + slot];
+                }
+            }
+        }
+        float h[S][8], w[S][8], p1[S], p2[S];
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            p1[k] = p2[k] = 0.f;
+            const bool live = active && (grp * S + k < B);
+            if (live) {
+                float z[8], d[8], cb[8], g[8], bt[8];
+                unpack8(xv[k], z);
+                unpack8(dv[k], d);
+                unpack8(cbv, cb);
+                unpack8(gv, g);
+                unpack8(bv, bt);
+                if (HAS_RES) {
+                    float r[8];
+                    unpack8(rv[k], r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] += r[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float hh = (z[j] + cb[j]) * rs[k] + nmr[k];
+                    const float gy = (hh * g[j] + bt[j] > 0.f) ? d[j] : 0.f; // relu'
+                    dg[j] += gy * hh;
+                    db[j] += gy;
+                    const float ww = gy * g[j];
+                    h[k][j] = hh;
+                    w[k][j] = ww;
+                    p1[k] += ww;
+                    p2[k] += ww * hh;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) h[k][j] = w[k][j] = 0.f;
+            }
+        }
+        // row sums: warp -> CTA -> every CTA of the cluster (distributed shared memory)
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                p1[k] += __shfl_xor_sync(0xffffffffu, p1[k], o);
+                p2[k] += __shfl_xor_sync(0xffffffffu, p2[k], o);
+            }
+            if (lane == 0) {
+                s_warp[warp][2 * k] = p1[k];
+                s_warp[warp][2 * k + 1] = p2[k];
+            }
+        }
+        __syncthreads();
+        // every CTA sends its 2*S sums to every CTA of the cluster (itself included); the receiver's
+        // mbarrier counts the bytes, so no cluster-wide barrier and no fence sits in this loop.
+        // Double buffering by parity is enough: a peer can be at most one group ahead, because it
+        // needs this CTA's sums of group g+1 (sent after all its warps left group g) to pass g+1.
+        const uint32_t bar = smem_u32(&s_bar[parity]);
+        if (tid == 0) mbar_expect_tx(bar, tx_bytes);
+        for (int i = tid; i < 2 * S * cs; i += kBwdThreads) {
+            const int v = i % (2 * S), dst = i / (2 * S);
+            float a = 0.f;
+#pragma unroll
+            for (int q = 0; q < kBwdThreads / 32; ++q) a += s_warp[q][v];
+            st_async_f32(map_to_rank(smem_u32(&s_peer[parity][rank][v]), (uint32_t)dst), a,
+                         map_to_rank(bar, (uint32_t)dst));
+        }
+        mbar_wait(bar, (it >> 1) & 1u);
+        float t = 0.f;
+        if (lane < 2 * S)
+            for (int r = 0; r < cs; ++r) t += s_peer[parity][r][lane];
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            const float a = __shfl_sync(0xffffffffu, t, 2 * k) * inv_d * rs[k];     // m1 * rstd
+            const float b = __shfl_sync(0xffffffffu, t, 2 * k + 1) * inv_d * rs[k]; // m2 * rstd
+            const int64_t smp = grp * S + k;
+            if (active && smp < B) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    o[j] = w[k][j] * rs[k] - a - h[k][j] * b;
+                    dcb[j] += o[j];
+                }
+                dx[smp * nvec + slot] = pack8(o);
+            }
+        }
+    }
+
+    if (active) {
+        float *out = partials + (size_t)cid * 2 * D + (size_t)slot * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            out[j] = dg[j];
+            out[D + j] = db[j];
+        }
+    }
+    // d(conv bias): fold the threads that share a channel group (tid % cvecs) through shared memory
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_cb[tid * 8 + j] = dcb[j];
+    __syncthreads();
+    const int C = cvecs * 8;
+    if (tid < C) {
+        const int grp = tid >> 3, j = tid & 7;
+        float sum = 0.f;
+        for (int q = grp; q < kBwdThreads; q += cvecs) sum += s_cb[q * 8 + j];
+        partials[(size_t)nclusters * 2 * D + (size_t)blockIdx.x * C + tid] = sum;
+    }
+    cluster_sync_all(); // no CTA leaves while a peer may still write into its shared memory
+}
+
+// sums the clustered backward's partials: thread i < 2D -> dgamma/dbeta (over clusters),
+// 2D <= i < 2D + C -> d conv bias (over CTAs)
+__global__ void reduce_cluster_partials_kernel(const float *__restrict__ partials, int nclusters, int nctas, int D,
+                                               int C, float *__restrict__ dgamma, float *__restrict__ dbeta,
+                                               float *__restrict__ dcbias)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * D) {
+        float s = 0.f;
+        for (int p = 0; p < nclusters; ++p) s += partials[(size_t)p * 2 * D + i];
+        if (i < D) dgamma[i] = s;
+        else dbeta[i - D] = s;
+    } else if (i < 2 * D + C && dcbias) {
+        const float *cbp = partials + (size_t)nclusters * 2 * D;
+        float s = 0.f;
+        for (int p = 0; p < nctas; ++p) s += cbp[(size_t)p * C + (i - 2 * D)];
+        dcbias[i - 2 * D] = s;
+    }
+}
+
 // Per-row transpose with dtype conversion: dst[r][b*A + a] = src[r][a*B + b] for a < A, b < B.
 // Used to bring the 19200 trunk columns of the fused head weight from the checkpoint's CHW order
 // (fp32 master) to the HWC order of the channels-last activations (bf16 working copy), and to
@@ -341,6 +584,50 @@ int sm_count_cached()
 
 } // namespace
 
+static int ln_relu_bwd_percta(const void *dy, const void *x, const void *res, const void *cbias, const void *gamma,
+                    const void *beta, const float *mean, const float *rstd, int64_t B, int32_t D, int32_t C,
+                    void *dx, float *dgamma, float *dbeta, float *dcbias, float *partials, void *stream)
+{
+    if (!dy || !x || !gamma || !beta || !mean || !rstd || !dx || !dgamma || !dbeta || !partials || B <= 0 ||
+        D <= 0 || D % 8)
+        return INV_ERR_INVALID_ARG;
+    if (C <= 0 || C % 8 || D % C || kLnThreads % (C / 8) || C > kLnThreads) return INV_ERR_INVALID_ARG;
+    const int cvecs = C / 8;
+    const int nvec = D / 8;
+    const int maxv = (nvec + kLnThreads - 1) / kLnThreads;
+    if (maxv > 5) return INV_ERR_INVALID_ARG;
+    const int nsm = sm_count_cached();
+    const unsigned grid = (unsigned)(B < nsm ? B : nsm); // one CTA per SM: 2*D floats of shared memory each
+    size_t smem = (size_t)2 * D * sizeof(float);
+    if (smem < (size_t)kLnThreads * 8 * sizeof(float)) smem = (size_t)kLnThreads * 8 * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(MV)                                                                                              \
+    if (res) {                                                                                                  \
+        cudaFuncSetAttribute(ln_relu_bwd_kernel<MV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        ln_relu_bwd_kernel<MV, true><<<grid, kLnThreads, smem, st>>>((const uint4 *)dy, (const uint4 *)x,       \
+            (const uint4 *)res, (const uint4 *)cbias, cvecs, (const uint4 *)gamma, (const uint4 *)beta, mean,    \
+            rstd, B, nvec, (uint4 *)dx, partials);                                                              \
+    } else {                                                                                                    \
+        cudaFuncSetAttribute(ln_relu_bwd_kernel<MV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        ln_relu_bwd_kernel<MV, false><<<grid, kLnThreads, smem, st>>>((const uint4 *)dy, (const uint4 *)x,      \
+            nullptr, (const uint4 *)cbias, cvecs, (const uint4 *)gamma, (const uint4 *)beta, mean, rstd, B,      \
+            nvec, (uint4 *)dx, partials);                                                                       \
+    }
+    switch (maxv) {
+    case 1: LAUNCH(1) break;
+    case 2: LAUNCH(2) break;
+    case 3: LAUNCH(3) break;
+    case 4: LAUNCH(4) break;
+    default: LAUNCH(5) break;
+    }
+#undef LAUNCH
+    if (cudaGetLastError() != cudaSuccess) return INV_ERR_CUDA;
+    const int width = 2 * D + C;
+    reduce_partials_kernel<<<(width + 255) / 256, 256, 0, st>>>(partials, (int)grid, width, dgamma, dbeta, dcbias, D);
+    return cudaGetLastError() == cudaSuccess ? INV_OK : INV_ERR_CUDA;
+}
+
+
 extern "C" {
 
 int inv_transpose_cast(const void *src, int32_t src_is_f32, int64_t ld_src, void *dst, int32_t dst_is_f32,
@@ -360,7 +647,7 @@ int inv_transpose_cast(const void *src, int32_t src_is_f32, int64_t ld_src, void
     return cudaGetLastError() == cudaSuccess ? INV_OK : INV_ERR_CUDA;
 }
 
-int inv_ln_relu_partials(int32_t D) { (void)D; return sm_count_cached(); }
+int inv_ln_relu_partials(int32_t D) { (void)D; return 2 * sm_count_cached(); }
 
 int inv_ln_relu_fwd(const void *x, const void *res, const void *cbias, const void *gamma, const void *beta,
                     int64_t B, int32_t D, int32_t C, float eps, void *y, float *mean, float *rstd, void *stream)
@@ -402,39 +689,63 @@ int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *
     if (!dy || !x || !gamma || !beta || !mean || !rstd || !dx || !dgamma || !dbeta || !partials || B <= 0 ||
         D <= 0 || D % 8)
         return INV_ERR_INVALID_ARG;
-    if (C <= 0 || C % 8 || D % C || kLnThreads % (C / 8) || C > kLnThreads) return INV_ERR_INVALID_ARG;
+    {   // INV_LN_BWD=cluster selects the cluster-split kernel (experiments); default: one CTA per SM
+        static int use_cluster = -1;
+        if (use_cluster < 0) {
+            const char *e = getenv("INV_LN_BWD");
+            use_cluster = (e && e[0] == 'c') ? 1 : 0;
+        }
+        if (!use_cluster)
+            return ln_relu_bwd_percta(dy, x, res, cbias, gamma, beta, mean, rstd, B, D, C, dx, dgamma, dbeta, dcbias,
+                                      partials, stream);
+    }
+    if (C <= 0 || C % 8 || D % C || kBwdThreads % (C / 8) || C > kBwdThreads) return INV_ERR_INVALID_ARG;
     const int cvecs = C / 8;
     const int nvec = D / 8;
-    const int maxv = (nvec + kLnThreads - 1) / kLnThreads;
-    if (maxv > 5) return INV_ERR_INVALID_ARG;
-    const int nsm = sm_count_cached();
-    const unsigned grid = (unsigned)(B < nsm ? B : nsm); // one CTA per SM: 2*D floats of shared memory each
-    size_t smem = (size_t)2 * D * sizeof(float);
-    if (smem < (size_t)kLnThreads * 8 * sizeof(float)) smem = (size_t)kLnThreads * 8 * sizeof(float);
+    const int cs = (nvec + kBwdThreads - 1) / kBwdThreads; // CTAs per cluster: 2 / 4 / 8 for D = 4800 / 9600 / 19200
+    if (cs > kMaxCluster) return INV_ERR_INVALID_ARG;      // D <= 20480
+    constexpr int S = 2;
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(MV)                                                                                              \
-    if (res) {                                                                                                  \
-        cudaFuncSetAttribute(ln_relu_bwd_kernel<MV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        ln_relu_bwd_kernel<MV, true><<<grid, kLnThreads, smem, st>>>((const uint4 *)dy, (const uint4 *)x,       \
-            (const uint4 *)res, (const uint4 *)cbias, cvecs, (const uint4 *)gamma, (const uint4 *)beta, mean,    \
-            rstd, B, nvec, (uint4 *)dx, partials);                                                              \
-    } else {                                                                                                    \
-        cudaFuncSetAttribute(ln_relu_bwd_kernel<MV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        ln_relu_bwd_kernel<MV, false><<<grid, kLnThreads, smem, st>>>((const uint4 *)dy, (const uint4 *)x,      \
-            nullptr, (const uint4 *)cbias, cvecs, (const uint4 *)gamma, (const uint4 *)beta, mean, rstd, B,      \
-            nvec, (uint4 *)dx, partials);                                                                       \
+    auto kern = res ? ln_relu_bwd_cluster_kernel<S, true> : ln_relu_bwd_cluster_kernel<S, false>;
+
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(kBwdThreads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // as many clusters as the GPU keeps resident at once (the work split is static per cluster)
+    static int resident[64][kMaxCluster + 1][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int ncl = 0;
+    if (dev >= 0 && dev < 64) ncl = resident[dev][cs][res ? 1 : 0];
+    if (ncl == 0) {
+        cfg.gridDim = dim3((unsigned)(cs * 64), 1, 1);
+        if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess || ncl <= 0) {
+            cudaGetLastError();
+            ncl = sm_count_cached() / cs; // conservative: one CTA per SM
+        }
+        const int cap = 2 * sm_count_cached() / cs; // the partials buffer holds 2 * SMs parts
+        if (ncl > cap) ncl = cap;
+        if (dev >= 0 && dev < 64) resident[dev][cs][res ? 1 : 0] = ncl;
     }
-    switch (maxv) {
-    case 1: LAUNCH(1) break;
-    case 2: LAUNCH(2) break;
-    case 3: LAUNCH(3) break;
-    case 4: LAUNCH(4) break;
-    default: LAUNCH(5) break;
-    }
-#undef LAUNCH
-    if (cudaGetLastError() != cudaSuccess) return INV_ERR_CUDA;
+    const int64_t groups = (B + S - 1) / S;
+    if (ncl > groups) ncl = (int)groups;
+    if (ncl < 1) ncl = 1;
+    cfg.gridDim = dim3((unsigned)(ncl * cs), 1, 1);
+    const uint4 *dy4 = (const uint4 *)dy, *x4 = (const uint4 *)x, *res4 = (const uint4 *)res, *cb4 = (const uint4 *)cbias;
+    const uint4 *g4 = (const uint4 *)gamma, *b4 = (const uint4 *)beta;
+    uint4 *dx4 = (uint4 *)dx;
+    if (cudaLaunchKernelEx(&cfg, kern, dy4, x4, res4, cb4, cvecs, g4, b4, mean, rstd, B, nvec, dx4, partials) != cudaSuccess)
+        return INV_ERR_CUDA;
     const int width = 2 * D + C;
-    reduce_partials_kernel<<<(width + 255) / 256, 256, 0, st>>>(partials, (int)grid, width, dgamma, dbeta, dcbias, D);
+    reduce_cluster_partials_kernel<<<(width + 255) / 256, 256, 0, st>>>(partials, ncl, ncl * cs, D, C, dgamma, dbeta, dcbias);
     return cudaGetLastError() == cudaSuccess ? INV_OK : INV_ERR_CUDA;
 }
 

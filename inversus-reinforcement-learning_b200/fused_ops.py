@@ -104,3 +104,98 @@ class _HeadWeightToHWC(torch.autograd.Function):
 def head_weight_to_hwc(w: torch.Tensor, channels: int, positions: int) -> torch.Tensor:
     """bf16 HWC-ordered copy of the first channels*positions columns of the fp32 head weight."""
     return _HeadWeightToHWC.apply(w, channels, positions)
+
+
+class PackedStates:
+    """Packed env states as the policy's input: `planes` is [5, M, 4] int32 (a view or copy of
+    `BatchedInversus.packed_state`, 80 bytes per env), `view` 0 = P1's perspective, 1 = P2's. The
+    policy's first block reads this directly (`encode_layer1`); no observation tensor exists."""
+
+    __slots__ = ("planes", "view")
+
+    def __init__(self, planes: torch.Tensor, view: int = 0):
+        assert planes.is_cuda and planes.dtype == torch.int32 and planes.dim() == 3 and planes.shape[0] == 5 \
+            and planes.shape[2] == 4 and planes.is_contiguous(), "packed planes must be a contiguous [5, M, 4] int32 CUDA tensor"
+        self.planes, self.view = planes, int(view)
+
+    @property
+    def shape(self):
+        return (self.planes.shape[1],)
+
+    def __len__(self):
+        return self.planes.shape[1]
+
+    def chunk(self, lo: int, hi: int) -> "PackedStates":
+        return _PackedSlice(self.planes, self.view, lo, hi)
+
+
+class _PackedSlice(PackedStates):
+    """Entries [lo, hi) of a PackedStates without copying (the kernels take a plane stride)."""
+
+    __slots__ = ("lo", "hi")
+
+    def __init__(self, planes, view, lo, hi):
+        self.planes, self.view, self.lo, self.hi = planes, view, int(lo), int(hi)
+
+    @property
+    def shape(self):
+        return (self.hi - self.lo,)
+
+    def __len__(self):
+        return self.hi - self.lo
+
+
+def _packed_args(ps: PackedStates):
+    stride = ps.planes.shape[1]
+    lo = getattr(ps, "lo", 0)
+    count = len(ps)
+    # entry lo of plane k sits at planes[k, lo]: offset the base pointer, keep the plane stride
+    return ps.planes.data_ptr() + lo * 16, stride, count
+
+
+class _EncodeLayer1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w1, b1, gamma_hwc, beta_hwc, ps, eps):
+        assert w1.is_cuda and w1.dtype == torch.float32 and tuple(w1.shape) == (32, 12, 3, 3)
+        w1, b1 = w1.contiguous(), b1.contiguous()
+        gamma_hwc, beta_hwc = gamma_hwc.contiguous(), beta_hwc.contiguous()
+        assert gamma_hwc.dtype == torch.float32 and gamma_hwc.numel() == 4800 and beta_hwc.numel() == 4800
+        ptr, stride, count = _packed_args(ps)
+        dev = w1.device
+        y = torch.empty((count, 4800), dtype=torch.bfloat16, device=dev)
+        extra = torch.empty((count, 4), dtype=torch.float32, device=dev)
+        mean = torch.empty(count, dtype=torch.float32, device=dev)
+        rstd = torch.empty(count, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _capi.check(_capi.load().inv_encode_fwd(ptr, stride, count, ps.view, w1.data_ptr(), b1.data_ptr(),
+                                                    gamma_hwc.data_ptr(), beta_hwc.data_ptr(), float(eps), y.data_ptr(),
+                                                    extra.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _stream(w1)))
+        ctx.save_for_backward(w1, b1, gamma_hwc, beta_hwc, mean, rstd)
+        ctx.ps = ps
+        ctx.mark_non_differentiable(extra)
+        return y, extra
+
+    @staticmethod
+    def backward(ctx, dy, _dextra):
+        w1, b1, gamma_hwc, beta_hwc, mean, rstd = ctx.saved_tensors
+        ps = ctx.ps
+        ptr, stride, count = _packed_args(ps)
+        dev = w1.device
+        dy = dy.contiguous()
+        lib = _capi.load()
+        dw1, db1 = torch.empty_like(w1), torch.empty_like(b1)
+        dg, db = torch.empty_like(gamma_hwc), torch.empty_like(beta_hwc)
+        with torch.cuda.device(dev):
+            partials = torch.empty(lib.inv_encode_partials_floats(), dtype=torch.float32, device=dev)
+            _capi.check(lib.inv_encode_bwd(ptr, stride, count, ps.view, w1.data_ptr(), b1.data_ptr(), gamma_hwc.data_ptr(),
+                                           beta_hwc.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dy.data_ptr(),
+                                           dw1.data_ptr(), db1.data_ptr(), dg.data_ptr(), db.data_ptr(),
+                                           partials.data_ptr(), _stream(w1)))
+        return dw1, db1, dg, db, None, None
+
+
+def encode_layer1(ps: PackedStates, w1: torch.Tensor, b1: torch.Tensor, gamma_hwc: torch.Tensor,
+                  beta_hwc: torch.Tensor, eps: float = 1e-5):
+    """relu(LayerNorm(conv1(observation(state)) + b1) * gamma + beta) straight from packed states:
+    returns (y [M, 4800] bf16 in HWC order, extra [M, 4] f32). fp32 master weights in, fp32 grads out."""
+    return _EncodeLayer1.apply(w1, b1, gamma_hwc, beta_hwc, ps, eps)

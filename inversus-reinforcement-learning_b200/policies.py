@@ -10,7 +10,7 @@ same weights in bf16, channels-last end to end, with the two 19204-wide head GEM
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -61,19 +61,29 @@ class InversusCNNPolicy(nn.Module):
         return self.fc_actor(x), self.fc_critic(x)
 
     # ------------------------------------------------------------------ bf16 tensor-core path
-    def _prepare_bf16(self) -> dict:
-        """bf16 working copies of the parameters in the layouts the fast path wants (differentiable
-        w.r.t. the fp32 masters): channels-last conv filters, HWC-ordered LayerNorm affines, and the
-        fused head matrix with its K dimension split into HWC-ordered trunk columns + padded extras."""
+    def _prepare_group(self, group: str) -> dict:
+        """bf16 working copies of one group of parameters in the layouts the fast path wants
+        (differentiable w.r.t. the fp32 masters). Groups: "l1" (block 1 evaluated from packed states:
+        fp32 masters + HWC LayerNorm affine), "c1".."c4" (channels-last conv filter, conv bias,
+        HWC-ordered LayerNorm affine), "head" (the fused head matrix with its K dimension split into
+        HWC-ordered trunk columns + padded extras, and the small head layers)."""
         bf = torch.bfloat16
         H, W, nf = self.height, self.width, self.feature_dim
         prep = {}
-        for i in (1, 2, 3, 4):
+        if group == "l1":  # csrc/encoder_kernels.cu reads the fp32 masters directly
+            prep["w1"], prep["b1"] = self.conv1.weight, self.conv1.bias
+            prep["g1_hwc"] = self.norm1.weight.permute(1, 2, 0).reshape(-1)
+            prep["be1_hwc"] = self.norm1.bias.permute(1, 2, 0).reshape(-1)
+            return prep
+        if group in ("c1", "c2", "c3", "c4"):
+            i = int(group[1])
             conv, norm = getattr(self, f"conv{i}"), getattr(self, f"norm{i}")
             prep[f"cw{i}"] = conv.weight.to(bf).contiguous(memory_format=torch.channels_last)
             prep[f"cb{i}"] = conv.bias.to(bf)
             prep[f"nw{i}"] = norm.weight.permute(1, 2, 0).to(bf).contiguous()
             prep[f"nb{i}"] = norm.bias.permute(1, 2, 0).to(bf).contiguous()
+            return prep
+        assert group == "head"
         a0, c0 = self.fc_actor[0], self.fc_critic[0]
         w0 = torch.cat([a0.weight, c0.weight], 0)                # [2*hidden, 19200 + extra]
         c = nf // (H * W)
@@ -91,14 +101,34 @@ class InversusCNNPolicy(nn.Module):
                 prep[f"{name}_b{k}"] = seq[k].bias.to(bf)
         return prep
 
-    def _forward_prepared(self, prep: dict, grid_tensor: torch.Tensor, extra_vector: torch.Tensor):
+    _PREP_GROUPS = ("l1", "c1", "c2", "c3", "c4", "head")
+
+    def _prepare_bf16(self) -> dict:
+        """All groups at once (what the inference cache holds)."""
+        prep = {}
+        for g in self._PREP_GROUPS:
+            prep.update(self._prepare_group(g))
+        return prep
+
+    def _forward_prepared(self, prep: dict, grid_tensor, extra_vector: Optional[torch.Tensor]):
         bf = torch.bfloat16
         H, W = self.height, self.width
-        x = grid_tensor.to(bf).contiguous(memory_format=torch.channels_last)
-        nb = x.shape[0]
-        fused = x.is_cuda and self.use_fused_kernels
+        packed = not isinstance(grid_tensor, torch.Tensor)       # fused_ops.PackedStates
+        if packed:
+            # block 1 (conv1 + bias + LayerNorm + ReLU) straight from the 80-byte env states: no
+            # observation tensor, no layout conversion, no K=108 convolution
+            from .fused_ops import encode_layer1
+            flat, extra_vector = encode_layer1(grid_tensor, prep["w1"], prep["b1"], prep["g1_hwc"], prep["be1_hwc"],
+                                               self.norm1.eps)
+            nb = flat.shape[0]
+            x = flat.view(nb, H, W, _CONV_WIDTHS[0]).permute(0, 3, 1, 2)
+            fused = True
+        else:
+            x = grid_tensor.to(bf).contiguous(memory_format=torch.channels_last)
+            nb = x.shape[0]
+            fused = x.is_cuda and self.use_fused_kernels
         res = None
-        for i in (1, 2, 3, 4):
+        for i in ((2, 3, 4) if packed else (1, 2, 3, 4)):
             # fused path: cuDNN runs bias-free, the per-channel bias is added inside the LayerNorm kernel
             y = F.conv2d(x, prep[f"cw{i}"], None if fused else prep[f"cb{i}"], padding=1)
             eps = getattr(self, f"norm{i}").eps
@@ -135,7 +165,10 @@ class InversusCNNPolicy(nn.Module):
         aligned rows, weight columns permuted to HWC order so activations are never transposed)
         and the 4 extra features. Accepts f32/bf16/u8 observation planes (they hold only 0/1).
         Returns fp32 logits and value."""
-        return self._forward_prepared(self._prepare_bf16(), grid_tensor, extra_vector)
+        # the working copies are made at their point of use: autograd then runs each conversion's
+        # backward right after the layer's own, so the head gradients (96 % of all bytes) are final
+        # -- and their all-reduce can start -- while backward is still in the trunk
+        return self._forward_prepared(_LazyPrep(self), grid_tensor, extra_vector)
 
     @torch.no_grad()
     def infer(self, grid_tensor: torch.Tensor, extra_vector: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -162,9 +195,25 @@ class InversusCNNPolicy(nn.Module):
         elif cache[0] != key:
             fresh = self._prepare_bf16()
             for k, v in cache[1].items():
-                v.copy_(fresh[k])
+                if fresh[k] is not v and fresh[k].data_ptr() != v.data_ptr():  # fp32 masters are cached as themselves
+                    v.copy_(fresh[k])
             cache[0] = key
         return cache[1]
+
+
+class _LazyPrep(dict):
+    """`prep[key]` prepares the parameter group that `key` belongs to on first use."""
+
+    _GROUP = {"w1": "l1", "b1": "l1", "g1_hwc": "l1", "be1_hwc": "l1"}
+    _GROUP.update({f"{k}{i}": f"c{i}" for i in (1, 2, 3, 4) for k in ("cw", "cb", "nw", "nb")})
+
+    def __init__(self, policy: InversusCNNPolicy):
+        super().__init__()
+        self._policy = policy
+
+    def __missing__(self, key):
+        self.update(self._policy._prepare_group(self._GROUP.get(key, "head")))
+        return dict.__getitem__(self, key)
 
 
 def make_policy_from_env(env=None) -> InversusCNNPolicy:

@@ -131,6 +131,9 @@ class DeviceRollout:
             T = self.t
             flat = self.packed[:, :T].reshape(5, T * self.N, 4)
             sel = flat.index_select(1, idx).contiguous()
+            if obs_dtype == "packed":  # the policy's encoder reads the 80-byte states directly
+                from .fused_ops import PackedStates
+                return PackedStates(sel, 0), None
             return sim.obs_from_packed(sel, view=0, obs_dtype=obs_dtype)
         T = self.t
         return (self.obs[:T].reshape(T * self.N, 12, 10, 15).index_select(0, idx),
@@ -147,7 +150,7 @@ class PPOAgent:
                  clip_ratio: float = 0.2, epochs: int = 4, batch_size: int = 512, entropy_coef: float = 0.02,
                  value_coef: float = 0.1, device: str = "cpu", *, gae_mode: str = "per_env",
                  precision: str = "fp32", shuffle: str = "torch", generator: Optional[torch.Generator] = None,
-                 graph_update: bool = False):
+                 graph_update: bool = False, packed_encoder: bool = False):
         assert gae_mode in ("per_env", "reference") and precision in ("fp32", "bf16") and shuffle in ("torch", "numpy")
         self.device = torch.device(device)
         self.policy = policy.to(self.device)
@@ -162,6 +165,13 @@ class PPOAgent:
         self.gae_mode, self.precision, self.shuffle, self.generator = gae_mode, precision, shuffle, generator
         self.max_grad_norm = 0.5  # ppo_agent.py:228
         self.act_chunk = 65536    # samples per inference micro-batch in act()
+        # packed_encoder: the policy's first block reads packed env states (csrc/encoder_kernels.cu);
+        # the update then never materialises observations
+        self.packed_encoder = bool(packed_encoder) and cuda and precision == "bf16"
+        self._flat_grad = None    # all gradients as views of one buffer (built on first use, CUDA only)
+        self.grad_buckets = 4     # NCCL all-reduces per minibatch, launched while backward still runs
+        self.comm_dtype = torch.float32  # torch.bfloat16 halves the all-reduce bytes (fp32 accumulation in Adam)
+        self.allreduce_ms = None  # filled by time_allreduce()
         self.reset_buffers()
 
     # ------------------------------------------------------------------ reference-shaped list buffers
@@ -195,6 +205,8 @@ class PPOAgent:
 
     # ------------------------------------------------------------------ acting
     def _forward(self, grid, extra, train: bool):
+        if not isinstance(grid, torch.Tensor):  # fused_ops.PackedStates: always the bf16 tensor-core path
+            return self.policy.forward_bf16(grid, None) if train else self.policy.infer(grid, None)
         if self.precision == "bf16" and grid.is_cuda:
             return self.policy.forward_bf16(grid, extra) if train else self.policy.infer(grid, extra)
         return self.policy(grid.float() if grid.dtype != torch.float32 else grid, extra)
@@ -203,13 +215,20 @@ class PPOAgent:
         """ppo_agent.py:68-106. numpy in -> numpy (actions, log_probs, values) like the reference;
         tensors in -> device tensors (no host round trip, no sync)."""
         self.policy.eval()
-        as_numpy = not isinstance(grid_tensors, torch.Tensor)
+        packed = hasattr(grid_tensors, "planes")  # fused_ops.PackedStates (extra_vectors is ignored)
+        as_numpy = not packed and not isinstance(grid_tensors, torch.Tensor)
         with torch.no_grad():
-            grid = torch.as_tensor(grid_tensors).to(self.device)
-            extra = torch.as_tensor(extra_vectors).to(self.device)
+            if packed:
+                grid, extra = grid_tensors, None
+            else:
+                grid = torch.as_tensor(grid_tensors).to(self.device)
+                extra = torch.as_tensor(extra_vectors).to(self.device)
             n = grid.shape[0]
             if n > self.act_chunk:  # bound activation memory: 1M envs x 19200 features would be 38 GB per layer
-                parts = [self._forward(grid[i:i + self.act_chunk], extra[i:i + self.act_chunk], train=False)
+                def part(i):
+                    j = min(i + self.act_chunk, n)
+                    return (grid.chunk(i, j), None) if packed else (grid[i:j], extra[i:j])
+                parts = [self._forward(*part(i), train=False)
                          for i in range(0, n, self.act_chunk)]
                 logits = torch.cat([p[0] for p in parts])
                 values = torch.cat([p[1] for p in parts])
@@ -229,20 +248,120 @@ class PPOAgent:
         return actions, log_probs, values
 
     # ------------------------------------------------------------------ update
+    @staticmethod
+    def _world() -> int:
+        d = torch.distributed
+        return d.get_world_size() if d.is_available() and d.is_initialized() else 1
+
+    def _setup_flat_grads(self) -> None:
+        """Every `p.grad` becomes a view of ONE persistent buffer, laid out in the order gradients
+        become ready in backward (heads first: their two 19204x256 matrices are 96 % of the bytes),
+        cut into `grad_buckets` contiguous buckets. Zeroing the gradients is one memset; under
+        torch.distributed each bucket is all-reduced (averaged) by NCCL as soon as its last
+        gradient has been accumulated, while backward is still running on the trunk."""
+        params = [p for p in reversed(list(self.policy.parameters())) if p.requires_grad]
+        total = sum(p.numel() for p in params)
+        flat = torch.zeros(total, dtype=params[0].dtype, device=params[0].device)
+        target = -(-total // max(int(self.grad_buckets), 1))
+        buckets, off, start, members = [], 0, 0, []
+        for p in params:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            members.append(p)
+            if off - start >= target or off == total:
+                buckets.append({"lo": start, "hi": off, "n": len(members), "pending": len(members), "work": None})
+                for q in members:
+                    q._inv_bucket = len(buckets) - 1
+                start, members = off, []
+        self._flat_grad, self._buckets, self._sync_active = flat, buckets, False
+        for p in params:
+            p.register_post_accumulate_grad_hook(self._grad_ready)
+
+    def _launch_bucket(self, b: dict) -> None:
+        d = torch.distributed
+        view = self._flat_grad[b["lo"]:b["hi"]]
+        if self.comm_dtype != view.dtype:  # narrower wire format: convert, reduce, convert back
+            wire = view.to(self.comm_dtype)
+            d.all_reduce(wire, op=d.ReduceOp.SUM)
+            view.copy_(wire)
+            b["work"] = None
+            return
+        avg = d.get_backend() == "nccl"
+        b["avg"] = avg
+        b["work"] = d.all_reduce(view, op=d.ReduceOp.AVG if avg else d.ReduceOp.SUM, async_op=True)
+
+    def _grad_ready(self, p) -> None:
+        if not self._sync_active:
+            return
+        b = self._buckets[p._inv_bucket]
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            self._launch_bucket(b)
+
+    def _begin_grad_sync(self) -> None:
+        self._sync_active = self._world() > 1
+        for b in self._buckets:
+            b["pending"], b["work"], b["avg"] = b["n"], None, True
+
+    def _finish_grad_sync(self) -> None:
+        """Wait for the bucket all-reduces launched from the backward hooks (and launch any bucket
+        whose gradients did not all arrive through a hook); leaves averaged gradients in place."""
+        if not self._sync_active:
+            return
+        self._sync_active = False
+        world = self._world()
+        for b in self._buckets:
+            if b["pending"] != 0:
+                self._launch_bucket(b)
+        for b in self._buckets:
+            if b["work"] is not None:
+                b["work"].wait()
+            if not b["avg"] or self.comm_dtype != self._flat_grad.dtype:
+                self._flat_grad[b["lo"]:b["hi"]].div_(world)
+
     def _sync_grads(self) -> None:
-        if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        """Blocking gradient average without the flat buffer (kept for callers that own .grad)."""
+        if self._world() == 1:
             return
-        if torch.distributed.get_world_size() == 1:
-            return
-        grads = [p.grad for p in self.policy.parameters() if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
-        flat.div_(torch.distributed.get_world_size())
-        off = 0
-        for g in grads:
-            n = g.numel()
-            g.copy_(flat[off:off + n].view_as(g))
-            off += n
+        world = self._world()
+        for p in self.policy.parameters():
+            if p.grad is not None:
+                torch.distributed.all_reduce(p.grad, op=torch.distributed.ReduceOp.SUM)
+                p.grad.div_(world)
+
+    def time_allreduce(self, iters: int = 20) -> Optional[dict]:
+        """Time the gradient all-reduce alone (all buckets, back to back): ms per minibatch and bytes."""
+        if self._world() == 1 or self._flat_grad is None:
+            return None
+        d = torch.distributed
+        dev = self._flat_grad.device
+        scratch = torch.zeros_like(self._flat_grad)
+        views = [scratch[b["lo"]:b["hi"]] for b in self._buckets]
+        for _ in range(3):
+            for v in views:
+                d.all_reduce(v)
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                for v in views:
+                    d.all_reduce(v)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / iters
+        else:
+            import time as _t
+            t0 = _t.perf_counter()
+            for _ in range(iters):
+                for v in views:
+                    d.all_reduce(v)
+            ms = (_t.perf_counter() - t0) * 1e3 / iters
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        d.all_reduce(t, op=d.ReduceOp.MAX)
+        self.allreduce_ms = float(t.item())
+        return {"allreduce_ms_per_minibatch": self.allreduce_ms, "bytes": scratch.numel() * scratch.element_size(),
+                "buckets": len(views), "dtype": str(scratch.dtype).replace("torch.", "")}
 
     def _permutation(self, n: int, state: dict) -> torch.Tensor:
         if self.shuffle == "numpy":
@@ -267,23 +386,33 @@ class PPOAgent:
         policy_loss = -torch.min(ratio * adv, torch.clamp(ratio, 1.0 - self.clip_ratio, 1.0 + self.clip_ratio) * adv).mean()
         value_loss = F.mse_loss(values.squeeze(-1), returns[idx])
         loss = policy_loss + self.value_coef * value_loss - self.entropy_coef * entropy
-        self.optimizer.zero_grad(set_to_none=True)
-        loss.backward()
-        self._sync_grads()
+        if self._flat_grad is None and (self.device.type == "cuda" or self._world() > 1):
+            self._setup_flat_grads()
+        if self._flat_grad is not None:
+            self._flat_grad.zero_()
+            self._begin_grad_sync()
+            loss.backward()
+            self._finish_grad_sync()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
+            loss.backward()
         torch.nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
         self.optimizer.step()
         sums += torch.stack([policy_loss.detach(), value_loss.detach(), entropy.detach()])
 
-    def _update_graph(self, n, fetch, actions, old_log_probs, advantages, returns):
+    def _update_graph(self, n, fetch, fetch_key, actions, old_log_probs, advantages, returns):
         """Static buffers + a CUDA graph of one full-size minibatch step (forward, loss, backward,
-        gradient clip, fused Adam). Warm-up steps needed for capture are undone afterwards."""
+        the bucketed NCCL gradient all-reduce when distributed, gradient clip, fused Adam). Warm-up
+        steps needed for capture are undone afterwards. The graph is reused only for the same
+        sample count, batch size and observation source (`fetch_key` names the tensors `fetch`
+        reads); anything else re-captures."""
         bs = self.batch_size
-        key = (n, bs, id(fetch.__self__) if hasattr(fetch, "__self__") else None)
-        if self._ug is not None and self._ug["n"] == n and self._ug["bs"] == bs:
+        key = (n, bs, fetch_key)
+        if self._ug is not None and self._ug["key"] == key:
             ug = self._ug
         else:
             dev = self.device
-            ug = self._ug = {"n": n, "bs": bs, "key": key, "graph": None,
+            ug = self._ug = {"key": key, "graph": None,
                              "idx": torch.zeros(bs, dtype=torch.int64, device=dev),
                              "sums": torch.zeros(3, device=dev),
                              "actions": torch.empty(n, dtype=torch.int64, device=dev),
@@ -294,15 +423,15 @@ class PPOAgent:
         ug["old_lp"].copy_(old_log_probs)
         ug["adv"].copy_(advantages)
         ug["ret"].copy_(returns)
-        ug["fetch"] = fetch
         if ug["graph"] is None:
+            ug["fetch"] = fetch
             params = list(self.policy.parameters())
             p_backup = [p.detach().clone() for p in params]
             o_backup = {p: {k: v.clone() for k, v in st.items() if torch.is_tensor(v)}
                         for p, st in self.optimizer.state.items()}
 
             def body():
-                self._minibatch_step(ug["idx"], lambda i: ug["fetch"](i), ug["actions"], ug["old_lp"], ug["adv"],
+                self._minibatch_step(ug["idx"], ug["fetch"], ug["actions"], ug["old_lp"], ug["adv"],
                                      ug["ret"], ug["sums"], validate=False)
             ug["idx"].copy_(torch.arange(bs, device=self.device) % n)
             side = torch.cuda.Stream(device=self.device)
@@ -312,7 +441,6 @@ class PPOAgent:
                     body()
             torch.cuda.current_stream(self.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            self.optimizer.zero_grad(set_to_none=True)
             with torch.cuda.graph(graph):
                 body()
             ug["graph"] = graph
@@ -330,21 +458,34 @@ class PPOAgent:
         return ug
 
     def _run_epochs(self, n: int, fetch: Callable[[torch.Tensor], Tuple[torch.Tensor, torch.Tensor]],
-                    actions, old_log_probs, advantages, returns) -> Dict[str, float]:
+                    actions, old_log_probs, advantages, returns, fetch_key=None) -> Dict[str, float]:
+        """`epochs` passes over shuffled minibatches (ppo_agent.py:192-231). Under torch.distributed
+        every rank runs the SAME number of optimisation steps (each contains collectives): the count
+        follows the largest shard, and a rank whose shard is one env smaller wraps its permutation
+        around so that its minibatches stay full."""
         self.policy.train()
-        distributed = (torch.distributed.is_available() and torch.distributed.is_initialized()
-                       and torch.distributed.get_world_size() > 1)
+        world = self._world()
+        n_steps_from = n
+        if world > 1:
+            t = torch.tensor([n], dtype=torch.int64, device=self.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            n_steps_from = int(t.item())
         ug = None
-        if self.graph_update and not distributed and self.shuffle == "torch" and n >= self.batch_size:
-            ug = self._update_graph(n, fetch, actions, old_log_probs, advantages, returns)
+        # the list path hands fresh tensors to every update (fetch_key None): nothing stable to capture
+        if self.graph_update and fetch_key is not None and self.shuffle == "torch" and n >= self.batch_size:
+            ug = self._update_graph(n, fetch, fetch_key, actions, old_log_probs, advantages, returns)
             ug["sums"].zero_()
         sums = ug["sums"] if ug is not None else torch.zeros(3, device=self.device)
         num_updates = 0
         perm_state: dict = {}
         for _ in range(self.epochs):
             perm = self._permutation(n, perm_state)
-            for start in range(0, n, self.batch_size):
+            if world > 1 and n_steps_from > n:  # smaller shard: wrap around (see docstring)
+                perm = torch.cat([perm, perm[:n_steps_from - n]])
+            for start in range(0, n_steps_from, self.batch_size):
                 idx = perm[start:start + self.batch_size]
+                if world > 1 and idx.numel() < self.batch_size and n >= self.batch_size:
+                    idx = torch.cat([idx, perm[:self.batch_size - idx.numel()]])  # same minibatch size on every rank
                 if ug is not None and idx.numel() == self.batch_size:
                     ug["idx"].copy_(idx)
                     ug["graph"].replay()
@@ -355,6 +496,18 @@ class PPOAgent:
             self.policy.mark_updated()  # fused optimizers do not bump tensor versions
         p, v, e = (sums / max(num_updates, 1)).tolist()  # the only host sync of the update
         return {"policy_loss": p, "value_loss": v, "entropy": e}
+
+    def _normalize_advantages(self, adv: torch.Tensor) -> torch.Tensor:
+        """ppo_agent.py:173 (numpy mean / std with ddof 0). Under torch.distributed the two moments
+        are taken over ALL ranks' samples, so the update does not depend on how envs are sharded."""
+        if self._world() == 1:
+            return (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-8)
+        m = torch.stack([adv.sum(dtype=torch.float64), (adv.double() ** 2).sum(),
+                         torch.tensor(float(adv.numel()), dtype=torch.float64, device=adv.device)])
+        torch.distributed.all_reduce(m, op=torch.distributed.ReduceOp.SUM)
+        mean = m[0] / m[2]
+        std = torch.sqrt(torch.clamp(m[1] / m[2] - mean * mean, min=0.0))
+        return ((adv - mean.float()) / (std.float() + 1e-8))
 
     def update(self, rollout: Optional[DeviceRollout] = None, sim=None, last_value: Optional[torch.Tensor] = None
                ) -> Dict[str, float]:
@@ -372,10 +525,16 @@ class PPOAgent:
         else:
             adv, ret = compute_gae(r, v, d, last_value, self.gamma, self.lam)
         adv, ret = adv.reshape(-1), ret.reshape(-1)
-        adv = (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-8)  # ppo_agent.py:173 (numpy std, ddof 0)
-        obs_dtype = "bf16" if self.precision == "bf16" else "f32"
+        adv = self._normalize_advantages(adv)
+        if self.packed_encoder and rollout.store == "packed":
+            obs_dtype = "packed"
+        else:
+            obs_dtype = "bf16" if self.precision == "bf16" else "f32"
+        src = rollout.packed if rollout.store == "packed" else rollout.obs
+        fetch_key = (obs_dtype, src.data_ptr(), T, N, None if sim is None else id(sim))
         stats = self._run_epochs(T * N, lambda idx: rollout.minibatch_obs(idx, sim, obs_dtype),
-                                 rollout.actions[:T].reshape(-1), rollout.log_probs[:T].reshape(-1), adv, ret)
+                                 rollout.actions[:T].reshape(-1), rollout.log_probs[:T].reshape(-1), adv, ret,
+                                 fetch_key=fetch_key)
         rollout.reset()
         return stats
 

@@ -98,9 +98,10 @@ class BatchedInversus:
         self.has_p2_view = bool(flags & _capi.FLAG_P2_VIEW)
         n = self.num_envs
         grid = (n, OBS_CHANNELS, BOARD_H, BOARD_W)
-        self.obs = self._view(_capi.BUF_OBS_P1, grid, obs=True)
+        self.has_obs = self._dt != _capi.OBS_DTYPE["none"]  # "none": consumers read packed_state (policy encoder)
+        self.obs = self._view(_capi.BUF_OBS_P1, grid, obs=True) if self.has_obs else None
         self.extra = self._view(_capi.BUF_EXTRA_P1, (n, 4), "<f4")
-        self.obs_p2 = self._view(_capi.BUF_OBS_P2, grid, obs=True) if self.has_p2_view else None
+        self.obs_p2 = self._view(_capi.BUF_OBS_P2, grid, obs=True) if self.has_p2_view and self.has_obs else None
         self.extra_p2 = self._view(_capi.BUF_EXTRA_P2, (n, 4), "<f4") if self.has_p2_view else None
         self.reward = self._view(_capi.BUF_REWARD, (n,), "<f4")
         self.done = self._view(_capi.BUF_DONE, (n,), "|u1")

@@ -71,7 +71,7 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
           rollout_steps: Optional[int] = None, batch_size: Optional[int] = None, epochs: int = 4, lr: float = 1e-4,
           reference_gae: bool = False, seed: Optional[int] = None, max_episode_steps: int = 500,
           save: bool = True, quiet: bool = False, cuda_graph: Optional[bool] = None,
-          graph_update: bool = True) -> dict:
+          graph_update: bool = True, packed_encoder: Optional[bool] = None, time_allreduce: bool = False) -> dict:
     """Shared body of train_vs_dummy / train_selfplay. `num_envs` is the GLOBAL env count; under
     torchrun each rank simulates its shard. Returns a summary dict (steps, episodes, win_rate,
     samples_per_s, ...)."""
@@ -90,8 +90,14 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
     selfplay = mode == "selfplay"
+    # bf16 runs feed the policy from the 80-byte packed states (csrc/encoder_kernels.cu): the
+    # simulator then keeps no observation tensor at all and a step moves ~200 bytes per env
+    if packed_encoder is None:
+        packed_encoder = precision == "bf16"
+    packed_encoder = bool(packed_encoder) and precision == "bf16"
     sim = BatchedInversus(n_local, "selfplay" if selfplay else "dummy", opponent_difficulty, max_episode_steps,
-                          seed=seed, device=dev.index, obs_dtype="bf16" if precision == "bf16" else "f32",
+                          seed=seed, device=dev.index,
+                          obs_dtype="none" if packed_encoder else ("bf16" if precision == "bf16" else "f32"),
                           auto_reset=True, env_id_base=first)
     policy = InversusCNNPolicy()
     if load_model:  # training.py:83-90
@@ -112,11 +118,21 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
     if batch_size is None:
         batch_size = 512 if num_envs * steps_per_env <= 1 << 16 else 16384
     agent = PPOAgent(policy, lr=lr, epochs=epochs, batch_size=batch_size, device=str(dev), precision=precision,
-                     gae_mode="reference" if reference_gae else "per_env", graph_update=graph_update and world == 1)
+                     gae_mode="reference" if reference_gae else "per_env", graph_update=graph_update,
+                     packed_encoder=packed_encoder)
     rollout = DeviceRollout(steps_per_env, n_local, dev, store="packed")
     logger = TrainingLogger(log_dir) if rank == 0 else None
 
-    obs, extra = sim.reset()
+    if packed_encoder:
+        from .fused_ops import PackedStates
+        view_p1, view_p2 = PackedStates(sim.packed_state, 0), PackedStates(sim.packed_state, 1)
+
+    def observe():
+        """What the policy acts on: the live packed state (encoder path) or the observation buffers."""
+        return (view_p1, None) if packed_encoder else (sim.obs, sim.extra)
+
+    sim.reset()
+    obs, extra = observe()
     step_count = last_log_step = last_opponent_update = episode_count = 0
     recent = deque(maxlen=100)  # (return, length, win) of the last 100 episodes (training.py:164-166)
     exact_recent = num_envs <= 256 and world == 1
@@ -143,11 +159,12 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
         # P2's view of the pre-step state (env_wrappers.py:311) is what the last step/reset emitted
         with torch.no_grad():
             fwd = target_policy.infer if precision == "bf16" else target_policy
-            if n_local > agent.act_chunk:
-                logits = torch.cat([fwd(sim.obs_p2[i:i + agent.act_chunk], sim.extra_p2[i:i + agent.act_chunk])[0]
-                                    for i in range(0, n_local, agent.act_chunk)])
+            ch = agent.act_chunk
+            if packed_encoder:
+                parts = [fwd(view_p2.chunk(i, min(i + ch, n_local)), None)[0] for i in range(0, n_local, ch)]
             else:
-                logits, _ = fwd(sim.obs_p2, sim.extra_p2)
+                parts = [fwd(sim.obs_p2[i:i + ch], sim.extra_p2[i:i + ch])[0] for i in range(0, n_local, ch)]
+            logits = parts[0] if len(parts) == 1 else torch.cat(parts)
             # Categorical(logits).sample() without its argument validation (a host sync that a CUDA
             # graph cannot capture); training.py:255-257
             return torch.multinomial(torch.softmax(logits, dim=-1), 1).squeeze(1).to(torch.int8)
@@ -176,7 +193,8 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
         t_dev.zero_()
         with torch.cuda.graph(step_graph):
             graphed_step()
-        obs, extra = sim.reset()  # warm-up and capture stepped the envs: start fresh episodes
+        sim.reset()  # warm-up and capture stepped the envs: start fresh episodes
+        obs, extra = observe()
         acc.zero_()
 
     while step_count < total_steps:
@@ -193,7 +211,8 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
             actions, log_probs, values = agent.act(obs, extra)
             rollout.store_pre(sim, actions, log_probs, values)
             a2 = opponent_actions() if selfplay else None
-            (obs, extra), rewards, dones, info = sim.step(actions.to(torch.int8), a2)
+            _, rewards, dones, info = sim.step(actions.to(torch.int8), a2)
+            obs, extra = observe()
             rollout.store_post(rewards, dones)
             d = dones.bool()
             acc += torch.stack([d.sum(), ((info & INFO_WIN) != 0).sum(),
@@ -245,8 +264,8 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
             else:
                 avg_reward, avg_len, win_rate = (rsum / ep, lsum / ep, wins / ep) if ep > 0 else (0.0, 0.0, 0.0)
             elapsed = time.time() - t_start
+            last_log_step = step_count  # on EVERY rank: the branch above contains a collective
             if rank == 0 and episode_count > 0:
-                last_log_step = step_count
                 logger.log(step_count, episode_count, avg_reward, win_rate, avg_len, update_stats.get("policy_loss", 0.0),
                            update_stats.get("value_loss", 0.0), update_stats.get("entropy", 0.0))
                 logger.log_perf(step_count, elapsed, step_count / elapsed, rollout_env_steps / max(rollout_time, 1e-9),
@@ -260,7 +279,9 @@ def train(mode: str = "vs_dummy", num_envs: int = 1, total_steps: int = 500_000,
     elapsed = time.time() - t_start
     if save and rank == 0:
         torch.save(policy.state_dict(), os.path.join(log_dir, "policy_final.pt"))  # training.py:199-200
-    summary = {"steps": step_count, "episodes": episode_count, "elapsed_s": elapsed,
+    allreduce = agent.time_allreduce() if (time_allreduce and world > 1) else None
+    summary = {"steps": step_count, "episodes": episode_count, "elapsed_s": elapsed, "allreduce": allreduce,
+               "packed_encoder": packed_encoder, "epochs": epochs,
                "samples_per_s": step_count / elapsed, "rollout_s": rollout_time, "update_s": update_time,
                "rollout_env_steps_per_s": rollout_env_steps / max(rollout_time, 1e-9),
                "win_rate": win_rate if episode_count else None, "avg_reward": avg_reward if episode_count else None,
@@ -278,7 +299,8 @@ def _steady(iters):
     """Throughput over the iterations after the first (which pays cuDNN/NCCL/allocator warm-up)."""
     body = iters[1:] if len(iters) > 1 else iters
     n, r, u = (sum(x[i] for x in body) for i in range(3))
-    return {"iterations": len(body), "samples_per_s": n / max(r + u, 1e-9), "rollout_env_steps_per_s": n / max(r, 1e-9),
+    return {"iterations": len(body), "samples": n, "rollout_s": r, "update_s": u,
+            "samples_per_s": n / max(r + u, 1e-9), "rollout_env_steps_per_s": n / max(r, 1e-9),
             "update_samples_per_s": n / max(u, 1e-9)}
 
 

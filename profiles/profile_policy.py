@@ -55,6 +55,49 @@ def train_step():
 
 ms = bench(train_step, 5)
 print(f"train minibatch B={B}: {ms:.3f} ms  {B / ms * 1e3 / 1e6:.3f} M samples/s")
+
+# ---- the packed-state path (round 2): block 1 straight from the 80-byte env states, no observation
+from inversus_b200 import BatchedInversus  # noqa: E402
+from inversus_b200.fused_ops import PackedStates  # noqa: E402
+
+for Bp in (8192, 65536):
+    sim = BatchedInversus(Bp, "dummy", "hard", 500, seed=0, obs_dtype="none")
+    sim.reset()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(0)
+    for _ in range(40):
+        sim.step(torch.randint(0, 13, (Bp,), device="cuda", generator=gen).to(torch.int8))
+    ps = PackedStates(sim.snapshot(), 0)
+    with torch.no_grad():
+        ms_p = bench(lambda: m.infer(ps, None))
+    print(f"infer from packed states B={Bp}: {ms_p:.3f} ms  {Bp / ms_p * 1e3 / 1e6:.2f} M samples/s  "
+          f"{Bp * 93e6 / (ms_p * 1e-3) / 1e12:.1f} TFLOP/s")
+    if Bp == 65536:
+        with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                m.infer(ps, None)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=70))
+    for Bt in ((8192, 32768) if Bp == 65536 else ()):
+        agent_p = PPOAgent(m, device="cuda", precision="bf16", batch_size=Bt, epochs=1, packed_encoder=True)
+        sel = ps.planes[:, :Bt].contiguous()
+        actp = torch.randint(0, 13, (Bt,), device="cuda")
+        advp, retp, olpp = torch.randn(Bt, device="cuda"), torch.randn(Bt, device="cuda"), -torch.rand(Bt, device="cuda")
+
+        def train_step_packed():
+            agent_p._run_epochs(Bt, lambda idx: (PackedStates(sel.index_select(1, idx).contiguous(), 0), None),
+                                actp, olpp, advp, retp)
+        ms_t = bench(train_step_packed, 5)
+        print(f"train minibatch from packed states B={Bt}: {ms_t:.3f} ms  {Bt / ms_t * 1e3 / 1e6:.3f} M samples/s  "
+              f"{Bt * 3 * 93e6 / (ms_t * 1e-3) / 1e12:.0f} TFLOP/s")
+        if Bt == 8192:
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for _ in range(3):
+                    train_step_packed()
+                torch.cuda.synchronize()
+            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=24, max_name_column_width=70))
+    sim.close()
+
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
         train_step()
