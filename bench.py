@@ -240,11 +240,56 @@ def run_oracle(args, n_envs, steps, warmup, budget_s=None):
     return {"value": n_envs * done_steps / dt, "seconds": dt, "steps": done_steps, "cores": cores}
 
 
+def run_reference_loop(args, seconds=4.0, n_envs=64):
+    """The reference's OWN Python step loop -- MultiEnvRunner.step (inversus_rl/env_wrappers.py:485-528)
+    plus the trainer's reset-on-done (inversus_rl/training.py:140-151) -- from the unmodified files
+    staged under oracle/_ref by oracle/make_ref.sh, timed on ONE host core. Returns None when the
+    staged copy is absent or the mode needs a policy callback (selfplay)."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if args.mode != "dummy" or not os.path.exists(os.path.join(ref, "inversus_rl", "env_wrappers.py")):
+        return None
+    import numpy as np
+    sys.path.insert(0, ref)
+    try:
+        from inversus_rl.env_wrappers import MultiEnvRunner  # the reference's module, not this repo's
+    finally:
+        sys.path.remove(ref)
+    runner = MultiEnvRunner(n_envs, "dummy", args.difficulty, args.max_episode_steps, seed=args.seed)
+    rs = np.random.RandomState(args.seed)
+    acts = rs.randint(0, 13, size=(64, n_envs))
+    runner.reset()
+
+    def one(k):
+        (grid, extra), _, dones, _ = runner.step(acts[k % 64])
+        for i in np.nonzero(dones)[0]:
+            g, e = runner.envs[i].reset()
+            grid[i], extra[i] = g, e
+    for k in range(3):
+        one(k)
+    t0 = time.perf_counter()
+    k = 0
+    while time.perf_counter() - t0 < seconds:
+        one(k)
+        k += 1
+    dt = time.perf_counter() - t0
+    try:
+        commit = open(os.path.join(ref, "SOURCE_COMMIT")).read().strip()
+    except OSError:
+        commit = "unknown"
+    return {"value": n_envs * k / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"{n_envs} envs x {k} steps ({dt:.1f} s), the reference's MultiEnvRunner.step + trainer-style "
+                      f"reset-on-done, unmodified files staged by oracle/make_ref.sh (commit {commit[:12]}), "
+                      f"stdlib Mersenne Twister draws, fp32 obs built every step"}
+
+
 def run_python_loop(args, seconds=4.0, n_envs=64):
     """The reference's PYTHON step loop, restated in oracle/py_loop.py with the reference's own data
     structures (pinned to the golden fixtures), timed on ONE host core: the number the north star
     asks to see beside the GPU result. The live reference measured 6.0e3 env-steps/s on one core of
     the builder container where this restatement measured 7.7e3."""
+    got = run_reference_loop(args, seconds, n_envs)
+    if got is not None:
+        return got
     import numpy as np
     from oracle.py_loop import PyRunner
     r = PyRunner(n_envs, args.mode, args.difficulty, args.max_episode_steps, seed=args.seed)
@@ -265,28 +310,86 @@ def run_python_loop(args, seconds=4.0, n_envs=64):
                       f"(oracle/py_loop.py), fp32 obs built every step, auto-reset"}
 
 
+def _ref_worker(ref_dir, n_envs, mode, difficulty, max_steps, seed, warmup, steps, barrier, out_q):
+    """One process of the reference arm: the staged reference's MultiEnvRunner, stepped like its trainer does."""
+    import numpy as np
+    sys.path.insert(0, ref_dir)
+    from inversus_rl.env_wrappers import MultiEnvRunner
+    runner = MultiEnvRunner(n_envs, mode, difficulty, max_steps, seed=seed)
+    rs = np.random.RandomState(seed)
+    acts = rs.randint(0, 13, size=(64, n_envs))
+    runner.reset()
+
+    def one(k):
+        (grid, extra), _, dones, _ = runner.step(acts[k % 64])
+        for i in np.nonzero(dones)[0]:  # inversus_rl/training.py:140-151
+            g, e = runner.envs[i].reset()
+            grid[i], extra[i] = g, e
+    for k in range(warmup):
+        one(k)
+    barrier.wait()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        one(warmup + k)
+    out_q.put(time.perf_counter() - t0)
+
+
+def run_reference_processes(args, warmup, steps, envs_per_proc=64):
+    """The unmodified reference (oracle/_ref) on ALL host cores: one process per core, each with its own
+    MultiEnvRunner over `envs_per_proc` envs. Returns None if the staged copy is missing."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if args.mode != "dummy" or not os.path.exists(os.path.join(ref, "inversus_rl", "env_wrappers.py")):
+        return None
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    barrier, q = ctx.Barrier(cores + 1), ctx.Queue()
+    procs = [ctx.Process(target=_ref_worker, args=(ref, envs_per_proc, "dummy", args.difficulty, args.max_episode_steps,
+                                                   args.seed + 1000 * i, warmup, steps, barrier, q)) for i in range(cores)]
+    for p in procs:
+        p.start()
+    barrier.wait()
+    t0 = time.perf_counter()
+    times = [q.get() for _ in procs]
+    dt = time.perf_counter() - t0
+    for p in procs:
+        p.join()
+    return {"value": cores * envs_per_proc * steps / dt, "seconds": dt, "steps": steps, "cores": cores,
+            "envs": cores * envs_per_proc, "slowest_worker_s": max(times)}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return 0
+    W = min(max(args.warmup, 3), 50)
+    # the CPU arm has no caches or clocks to settle: its warm-up is capped, and each "step" is one
+    # MultiEnvRunner.step over a bounded sample of the workload's envs (64 per host core)
+    steps = min(args.steps, 400)
+    ref = run_reference_processes(args, W, steps)
     n = args.cpu_sample_envs
-    # bounded sample: the CPU arm steps 65 536 of the workload's envs; its warm-up is capped (it has
-    # no caches or clocks to settle) and the run stops after 150 s whatever --steps asks for
-    r = run_oracle(args, n, args.steps, min(max(args.warmup, 3), 50), budget_s=150.0)
-    sample = (f"{n} envs (global ids 0..{n - 1} of the {args.envs_per_gpu}-env workload) x {r['steps']} steps, "
-              f"fp32 obs written every step, auto-reset, {r['cores']} pthreads")
+    port = run_oracle(args, n, args.steps, W, budget_s=20.0 if ref else 150.0)
+    port_line = {"value": port["value"], "unit": UNIT, "cores": port["cores"], "kind": "port",
+                 "sample": f"{n} envs x {port['steps']} steps through oracle/inversus_oracle.c (the C restatement), "
+                           f"fp32 obs written every step, auto-reset, {port['cores']} pthreads"}
+    if ref:
+        r, kind = ref, "reference"
+        sample = (f"{ref['envs']} envs ({ref['cores']} processes x 64) x {ref['steps']} steps of the same workload through the "
+                  f"reference's own MultiEnvRunner.step + reset-on-done (unmodified files staged by oracle/make_ref.sh), "
+                  f"fp32 obs built every step, one process per host core")
+    else:
+        r, kind, sample = port, "port", port_line["sample"]
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": r["steps"], "warmup": min(max(args.warmup, 3), 50), "ms_per_step": 1e3 * r["seconds"] / max(r["steps"], 1),
+        "steps": r["steps"], "warmup": W, "ms_per_step": 1e3 * r["seconds"] / max(r["steps"], 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": kind, "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "python_loop": run_python_loop(args, seconds=3.0),
+        "c_port": port_line,
         "gpu_launches": 0,
-        "note": "reference is pure Python (cannot travel to the GPU box); this is its algorithm restated in C "
-                "(oracle/inversus_oracle.c) on all host cores. Python reference measured in the builder "
-                "container: ~5e3 env-steps/s per core (SURVEY.md section 6).",
+        "note": "kind=reference: the reference's pure-Python step loop itself, on every host core of this box. "
+                "c_port: the same algorithm restated in C (oracle/inversus_oracle.c), for scale.",
     }
     emit(line)
     return 0
@@ -525,10 +628,20 @@ def main():
     if rank == 0 and world == 1 and args.cpu_seconds > 0:
         nc = args.cpu_sample_envs
         r = run_oracle(args, nc, 10 ** 9, 3, budget_s=args.cpu_seconds)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": f"{nc} envs x {r['steps']} steps ({r['seconds']:.1f} s) of the same workload through "
-                         f"oracle/inversus_oracle.c, fp32 obs written every step, {r['cores']} pthreads",
-               "python_loop": run_python_loop(args, seconds=min(4.0, args.cpu_seconds))}
+        port = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                "sample": f"{nc} envs x {r['steps']} steps ({r['seconds']:.1f} s) of the same workload through "
+                          f"oracle/inversus_oracle.c, fp32 obs written every step, {r['cores']} pthreads"}
+        # the reference itself (unmodified Python, oracle/_ref) on every host core: ~15 ms per step of 64 envs per core
+        ref = run_reference_processes(args, 5, max(20, int(args.cpu_seconds / 0.016)))
+        if ref:
+            cpu = {"value": ref["value"], "unit": UNIT, "cores": ref["cores"], "kind": "reference",
+                   "sample": f"{ref['envs']} envs ({ref['cores']} processes x 64) x {ref['steps']} steps ({ref['seconds']:.1f} s) of "
+                             f"the same workload through the reference's own MultiEnvRunner.step + reset-on-done "
+                             f"(unmodified files staged by oracle/make_ref.sh), one process per host core",
+                   "c_port": port}
+        else:
+            cpu = dict(port)
+        cpu["python_loop"] = run_python_loop(args, seconds=min(4.0, args.cpu_seconds))
 
     # ------------------------------------------------------------------ PPO block (all ranks)
     ppo = None

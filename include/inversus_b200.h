@@ -263,6 +263,16 @@ int inv_encode_bwd(const void *packed_dev, int64_t stride, int64_t count, int vi
                    const float *gamma_hwc, const float *beta_hwc, const float *mean, const float *rstd, const void *dy,
                    float *dw1, float *db1, float *dgamma_hwc, float *dbeta_hwc, float *partials, void *stream);
 
+/* Weight gradient of a 3x3, padding-1 convolution over the 15 x 10 board on the tcgen05 tensor cores
+ * (csrc/wgrad_kernels.cu), for the policy's conv3 / conv4 (inversus_rl/policies.py:36-43):
+ *   dw[co][ky][kx][ci] = sum over (n, y, x) of dy[n, y, x, co] * x[n, y + ky - 1, x + kx - 1, ci]
+ * dy: [B,10,15,cout] bf16 and x: [B,10,15,cin] bf16, both channels-last and 16-byte aligned;
+ * cout = 128, cin = 64 or 128. dw: [cout][3][3][cin] fp32 (the memory order of a channels-last
+ * filter). partials: scratch of inv_conv3x3_wgrad_scratch_floats(cin) floats. Deterministic. */
+int64_t inv_conv3x3_wgrad_scratch_floats(int32_t cin);
+int inv_conv3x3_wgrad(const void *dy, const void *x, int64_t B, int32_t cin, int32_t cout, float *dw, float *partials,
+                      void *stream);
+
 /* Per-row transpose + fp32<->bf16 conversion: dst[r][b*A + a] = src[r][a*B + b], a < A, b < B, for
  * `rows` rows with leading dimensions ld_src / ld_dst (elements). Exactly one side is fp32, the
  * other bf16. Carries the head weight of policies.py:61-75 between the checkpoint's CHW column

@@ -17,7 +17,6 @@
 // 0.24-0.41 of the HBM peak). The two per-sample row sums of the LayerNorm backward are combined
 // across the cluster through distributed shared memory, two samples per cluster barrier. Partials
 // are written per cluster and reduced by a second small kernel -- deterministic, no atomics.
-#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -351,13 +350,37 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// 1-D bulk copy global -> this CTA's shared memory, completion counted in bytes on an mbarrier (TMA)
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
-// Clustered backward. Grid = nclusters * CS CTAs of kBwdThreads threads; cluster c walks over sample
-// groups c, c + nclusters, ... of S samples each. Thread `slot = rank * kBwdThreads + tid` owns
-// columns [8*slot, 8*slot + 8) of every sample.
+// Clustered backward (round 2). Grid = nclusters * CS CTAs of kBwdThreads threads; cluster c walks
+// over sample groups c, c + nclusters, ... of S samples each. Thread `slot = rank * kBwdThreads +
+// tid` owns columns [8*slot, 8*slot + 8) of every sample: gamma/beta/conv-bias and the three
+// gradient accumulators of those columns are registers for the whole kernel.
+//
+// Software pipeline, one group deep. Iteration i runs
+//   pass 1 of group i    row sums s1, s2 + dgamma/dbeta accumulation; the CTA's partial sums go to
+//                        every CTA of the cluster with st.async into distributed shared memory,
+//                        counted by the receiver's mbarrier (no cluster barrier, no fence);
+//   pass 2 of group i-1  whose cluster-wide sums have had a whole pass to arrive: dx and d(bias).
+// The inputs of a group (x, dy, residual slices of S samples) are brought in by TMA bulk copies
+// into a 3-stage shared-memory ring, two groups ahead of their use, so both passes read shared
+// memory and HBM streams continuously. Pass 2 recomputes h and w from the ring instead of holding
+// them in registers (96 registers per thread => two CTAs per SM).
 // partials layout (floats): [nclusters][2][D] (dgamma, dbeta) followed by [grid][C] (d conv bias).
 constexpr int kBwdThreads = 320;
 constexpr int kMaxCluster = 8;
+constexpr int kBwdStages = 3;
+constexpr int kSumSlots = 4; // a peer can run up to two groups ahead of the slowest reader (see below)
+
+template <int S, bool HAS_RES>
+constexpr size_t bwd_cluster_smem() { return (size_t)kBwdStages * S * (HAS_RES ? 3 : 2) * kBwdThreads * 16; }
 
 template <int S, bool HAS_RES>
 __global__ void __launch_bounds__(kBwdThreads, 2)
@@ -367,140 +390,177 @@ ln_relu_bwd_cluster_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict
                            const float *__restrict__ rstd_in, int64_t B, int nvec, uint4 *__restrict__ dx,
                            float *__restrict__ partials)
 {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int cs = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-    __shared__ __align__(8) uint64_t s_bar[2]; // one mbarrier per parity: counts the peers' row-sum bytes
+    constexpr int NT = HAS_RES ? 3 : 2;
+    uint32_t cs, rank;
+    asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(cs));
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int nclusters = gridDim.x / cs, cid = blockIdx.x / cs;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int slot = rank * kBwdThreads + tid;
     const bool active = slot < nvec;
     const int D = nvec * 8;
     const float inv_d = 1.0f / (float)D;
+    const int myvec = min(kBwdThreads, nvec - (int)rank * kBwdThreads); // > 0 by construction of cs
+    const uint32_t slice_bytes = (uint32_t)myvec * 16u;
 
-    __shared__ float s_peer[2][kMaxCluster][2 * S]; // [parity][source rank][row sums], written by the peers
+    extern __shared__ __align__(128) unsigned char dsm[];
+    uint4 *ring = reinterpret_cast<uint4 *>(dsm); // [stage][sample][tensor][kBwdThreads]
+    __shared__ __align__(8) uint64_t s_full[kBwdStages]; // TMA completion per ring stage
+    __shared__ __align__(8) uint64_t s_sum[kSumSlots];   // peers' row-sum bytes per group slot
+    __shared__ float s_peer[kSumSlots][kMaxCluster][2 * S];
     __shared__ float s_warp[kBwdThreads / 32][2 * S];
     __shared__ float s_cb[kBwdThreads * 8];
 
-    // gamma, beta and the conv bias of this thread's 8 columns stay packed (4 registers each) and are
-    // unpacked where used: 96 registers per thread is what lets two CTAs share an SM
+    // gamma, beta and the conv bias of this thread's 8 columns stay packed (4 registers each);
+    // kBwdThreads % cvecs == 0, so slot % cvecs == tid % cvecs
     const uint4 gv = active ? gamma[slot] : make_uint4(0u, 0u, 0u, 0u);
     const uint4 bv = active ? beta[slot] : make_uint4(0u, 0u, 0u, 0u);
-    // kBwdThreads % cvecs == 0, so slot % cvecs == tid % cvecs
     const uint4 cbv = cbias ? cbias[tid % cvecs] : make_uint4(0u, 0u, 0u, 0u);
     float dg[8], db[8], dcb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) dg[j] = db[j] = dcb[j] = 0.f;
 
+    const int64_t groups = (B + S - 1) / S;
+    const int G = cid < groups ? (int)((groups - cid + nclusters - 1) / nclusters) : 0; // same in every CTA of the cluster
+
+    auto stage_ptr = [&](int stage, int k, int t) { return ring + ((size_t)(stage * S + k) * NT + t) * kBwdThreads; };
+    auto issue = [&](int i) { // thread 0: TMA loads of this CTA's column slice of group i
+        const int64_t grp = cid + (int64_t)i * nclusters;
+        const int stage = i % kBwdStages;
+        const int nvalid = (int)min((int64_t)S, B - grp * S);
+        const uint32_t bar = smem_u32(&s_full[stage]);
+        mbar_expect_tx(bar, (uint32_t)nvalid * NT * slice_bytes);
+        for (int k = 0; k < nvalid; ++k) {
+            const int64_t off = (grp * S + k) * nvec + (int64_t)rank * kBwdThreads;
+            bulk_load(smem_u32(stage_ptr(stage, k, 0)), x + off, slice_bytes, bar);
+            bulk_load(smem_u32(stage_ptr(stage, k, 1)), dy + off, slice_bytes, bar);
+            if (HAS_RES) bulk_load(smem_u32(stage_ptr(stage, k, 2)), res + off, slice_bytes, bar);
+        }
+    };
+
     if (tid == 0) {
-        mbar_init(smem_u32(&s_bar[0]), 1);
-        mbar_init(smem_u32(&s_bar[1]), 1);
+        for (int q = 0; q < kBwdStages; ++q) mbar_init(smem_u32(&s_full[q]), 1);
+        for (int q = 0; q < kSumSlots; ++q) mbar_init(smem_u32(&s_sum[q]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster_sync_all(); // every CTA's barriers exist before any peer signals them
-    const uint32_t tx_bytes = (uint32_t)(2 * S * cs * sizeof(float));
+    if (tid == 0) {
+        if (G > 0) issue(0);
+        if (G > 1) issue(1);
+    }
+    const uint32_t sum_bytes = (uint32_t)(2 * S * cs * sizeof(float));
+    uint32_t mask_cur[S], mask_prev[S]; // relu' bits of this thread's 8 columns, per sample of the group
+#pragma unroll
+    for (int k = 0; k < S; ++k) mask_cur[k] = mask_prev[k] = 0u;
 
-    const int64_t groups = (B + S - 1) / S;
-    int parity = 0;
-    uint32_t it = 0;
-    for (int64_t grp = cid; grp < groups; grp += nclusters, parity ^= 1, ++it) {
-        uint4 xv[S], dv[S], rv[HAS_RES ? S : 1];
-        float rs[S], nmr[S];
+    for (int i = 0; i <= G; ++i) {
+        if (i < G) { // ---------------------------------------------------------------- pass 1, group i
+            const int64_t grp = cid + (int64_t)i * nclusters;
+            const int stage = i % kBwdStages;
+            mbar_wait(smem_u32(&s_full[stage]), (uint32_t)(i / kBwdStages) & 1u);
+            float p1[S], p2[S];
 #pragma unroll
-        for (int k = 0; k < S; ++k) { // all global loads of the group first
-            const int64_t smp = grp * S + k;
-            if (smp < B) {
-                rs[k] = rstd_in[smp];
-                nmr[k] = -mean_in[smp] * rs[k];
-                if (active) {
-                    xv[k] = x[smp * nvec + slot];
-                    dv[k] = dy[smp * nvec + slot];
-                    if (HAS_RES) rv[k] = res[smp * nvec + slot];
+            for (int k = 0; k < S; ++k) {
+                p1[k] = p2[k] = 0.f;
+                mask_cur[k] = 0u;
+                const int64_t smp = grp * S + k;
+                if (active && smp < B) {
+                    const float rs = rstd_in[smp], nmr = -mean_in[smp] * rs;
+                    float z[8], d[8], cb[8], g[8], bt[8];
+                    unpack8(stage_ptr(stage, k, 0)[tid], z);
+                    unpack8(stage_ptr(stage, k, 1)[tid], d);
+                    unpack8(cbv, cb);
+                    unpack8(gv, g);
+                    unpack8(bv, bt);
+                    if (HAS_RES) {
+                        float r[8];
+                        unpack8(stage_ptr(stage, k, 2)[tid], r);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) z[j] += r[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float hh = (z[j] + cb[j]) * rs + nmr;
+                        const bool on = hh * g[j] + bt[j] > 0.f; // relu'
+                        const float gy = on ? d[j] : 0.f;
+                        mask_cur[k] |= on ? (1u << j) : 0u;
+                        dg[j] += gy * hh;
+                        db[j] += gy;
+                        const float ww = gy * g[j];
+                        p1[k] += ww;
+                        p2[k] += ww * hh;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    p1[k] += __shfl_xor_sync(0xffffffffu, p1[k], o);
+                    p2[k] += __shfl_xor_sync(0xffffffffu, p2[k], o);
+                }
+                if (lane == 0) {
+                    s_warp[warp][2 * k] = p1[k];
+                    s_warp[warp][2 * k + 1] = p2[k];
+                }
+            }
+            __syncthreads();
+            // This CTA's 2*S sums go to every CTA of the cluster (itself included). The receiver's
+            // mbarrier counts the bytes. Slot = i mod 4: a peer may already be sending group i+2
+            // while the slowest CTA still reads group i-1 (it cannot pass pass-2 of group i+1
+            // without that CTA's sums of i+1, which are sent after its pass-2 of i-1).
+            const int q = i % kSumSlots;
+            const uint32_t bar = smem_u32(&s_sum[q]);
+            if (tid == 0) mbar_expect_tx(bar, sum_bytes);
+            for (int e = tid; e < 2 * S * (int)cs; e += kBwdThreads) {
+                const int v = e % (2 * S), dst = e / (2 * S);
+                float a = 0.f;
+#pragma unroll
+                for (int w = 0; w < kBwdThreads / 32; ++w) a += s_warp[w][v];
+                st_async_f32(map_to_rank(smem_u32(&s_peer[q][rank][v]), (uint32_t)dst), a, map_to_rank(bar, (uint32_t)dst));
+            }
+        }
+        if (i >= 1) { // ------------------------------------------------------------- pass 2, group i-1
+            const int ip = i - 1;
+            const int64_t grp = cid + (int64_t)ip * nclusters;
+            const int stage = ip % kBwdStages, q = ip % kSumSlots;
+            mbar_wait(smem_u32(&s_sum[q]), (uint32_t)(ip / kSumSlots) & 1u);
+            float t = 0.f;
+            if (lane < 2 * S)
+                for (int r = 0; r < (int)cs; ++r) t += s_peer[q][r][lane];
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+                const float t1 = __shfl_sync(0xffffffffu, t, 2 * k), t2 = __shfl_sync(0xffffffffu, t, 2 * k + 1);
+                const int64_t smp = grp * S + k;
+                if (active && smp < B) {
+                    const float rs = rstd_in[smp], nmr = -mean_in[smp] * rs;
+                    const float a = t1 * inv_d * rs, b = t2 * inv_d * rs; // m1 * rstd, m2 * rstd
+                    float z[8], d[8], cb[8], g[8], o[8];
+                    unpack8(stage_ptr(stage, k, 0)[tid], z);
+                    unpack8(stage_ptr(stage, k, 1)[tid], d);
+                    unpack8(cbv, cb);
+                    unpack8(gv, g);
+                    if (HAS_RES) {
+                        float r[8];
+                        unpack8(stage_ptr(stage, k, 2)[tid], r);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) z[j] += r[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float hh = (z[j] + cb[j]) * rs + nmr;
+                        const float ww = ((mask_prev[k] >> j) & 1u) ? d[j] * g[j] : 0.f;
+                        o[j] = ww * rs - a - hh * b;
+                        dcb[j] += o[j];
+                    }
+                    dx[smp * nvec + slot] = pack8(o);
                 }
             }
         }
-        float h[S][8], w[S][8], p1[S], p2[S];
 #pragma unroll
-        for (int k = 0; k < S; ++k) {
-            p1[k] = p2[k] = 0.f;
-            const bool live = active && (grp * S + k < B);
-            if (live) {
-                float z[8], d[8], cb[8], g[8], bt[8];
-                unpack8(xv[k], z);
-                unpack8(dv[k], d);
-                unpack8(cbv, cb);
-                unpack8(gv, g);
-                unpack8(bv, bt);
-                if (HAS_RES) {
-                    float r[8];
-                    unpack8(rv[k], r);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) z[j] += r[j];
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float hh = (z[j] + cb[j]) * rs[k] + nmr[k];
-                    const float gy = (hh * g[j] + bt[j] > 0.f) ? d[j] : 0.f; // relu'
-                    dg[j] += gy * hh;
-                    db[j] += gy;
-                    const float ww = gy * g[j];
-                    h[k][j] = hh;
-                    w[k][j] = ww;
-                    p1[k] += ww;
-                    p2[k] += ww * hh;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) h[k][j] = w[k][j] = 0.f;
-            }
-        }
-        // row sums: warp -> CTA -> every CTA of the cluster (distributed shared memory)
-#pragma unroll
-        for (int k = 0; k < S; ++k) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                p1[k] += __shfl_xor_sync(0xffffffffu, p1[k], o);
-                p2[k] += __shfl_xor_sync(0xffffffffu, p2[k], o);
-            }
-            if (lane == 0) {
-                s_warp[warp][2 * k] = p1[k];
-                s_warp[warp][2 * k + 1] = p2[k];
-            }
-        }
-        __syncthreads();
-        // every CTA sends its 2*S sums to every CTA of the cluster (itself included); the receiver's
-        // mbarrier counts the bytes, so no cluster-wide barrier and no fence sits in this loop.
-        // Double buffering by parity is enough: a peer can be at most one group ahead, because it
-        // needs this CTA's sums of group g+1 (sent after all its warps left group g) to pass g+1.
-        const uint32_t bar = smem_u32(&s_bar[parity]);
-        if (tid == 0) mbar_expect_tx(bar, tx_bytes);
-        for (int i = tid; i < 2 * S * cs; i += kBwdThreads) {
-            const int v = i % (2 * S), dst = i / (2 * S);
-            float a = 0.f;
-#pragma unroll
-            for (int q = 0; q < kBwdThreads / 32; ++q) a += s_warp[q][v];
-            st_async_f32(map_to_rank(smem_u32(&s_peer[parity][rank][v]), (uint32_t)dst), a,
-                         map_to_rank(bar, (uint32_t)dst));
-        }
-        mbar_wait(bar, (it >> 1) & 1u);
-        float t = 0.f;
-        if (lane < 2 * S)
-            for (int r = 0; r < cs; ++r) t += s_peer[parity][r][lane];
-#pragma unroll
-        for (int k = 0; k < S; ++k) {
-            const float a = __shfl_sync(0xffffffffu, t, 2 * k) * inv_d * rs[k];     // m1 * rstd
-            const float b = __shfl_sync(0xffffffffu, t, 2 * k + 1) * inv_d * rs[k]; // m2 * rstd
-            const int64_t smp = grp * S + k;
-            if (active && smp < B) {
-                float o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    o[j] = w[k][j] * rs[k] - a - h[k][j] * b;
-                    dcb[j] += o[j];
-                }
-                dx[smp * nvec + slot] = pack8(o);
-            }
-        }
+        for (int k = 0; k < S; ++k) mask_prev[k] = mask_cur[k];
+        __syncthreads(); // ring stage (i-1) % 3 and s_warp are free again
+        if (tid == 0 && i + 2 < G) issue(i + 2);
     }
 
     if (active) {
@@ -714,8 +774,10 @@ int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *
     attr[0].val.clusterDim.x = (unsigned)cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    const size_t smem = res ? bwd_cluster_smem<S, true>() : bwd_cluster_smem<S, false>();
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return INV_ERR_CUDA;
     cfg.blockDim = dim3(kBwdThreads, 1, 1);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = 1;

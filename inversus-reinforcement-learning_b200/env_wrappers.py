@@ -23,7 +23,8 @@ from typing import Any, Dict, Optional, Tuple
 
 import numpy as np
 
-from .constants import BOARD_H, BOARD_W, INFO_GOT_HIT, INFO_LANDED_HIT, INFO_LOSE, INFO_WIN
+from .constants import (BOARD_H, BOARD_W, INFO_GOT_HIT, INFO_LANDED_HIT, INFO_LOSE, INFO_WIN, STREAM_RESET,
+                        TABLE_RESET_OFF, TABLE_STRIDE)
 from .simulator import BatchedInversus
 
 # (type, direction) names of the reference's Action dataclass (game_types.py:21-49)
@@ -103,6 +104,38 @@ def build_observation(env: "_EngineView", player_id=PlayerId.P1) -> Tuple[np.nda
     return grid[0].cpu().numpy(), extra[0].cpu().numpy()
 
 
+def _seeded_reset_draws(seed: int) -> np.ndarray:
+    """The 42 spawn draws of one reset as a pure function of `seed` alone: Philox4x32-10 with key =
+    the 64-bit seed and counter (0, 0, STREAM_RESET, block). Random numbers only -- the spawn
+    logic that consumes them stays in the reset kernel (injected-draw mode of the C ABI)."""
+    m32 = 0xFFFFFFFF
+    s = int(seed) & 0xFFFFFFFFFFFFFFFF
+    out = []
+    for blk in range(11):  # 44 >= 2 + 2*20 draws (core.py:69-90)
+        c0, c1, c2, c3 = 0, 0, STREAM_RESET, blk
+        k0, k1 = s & m32, s >> 32
+        for _ in range(10):
+            p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+            c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & m32, p1 & m32, ((p0 >> 32) ^ c3 ^ k1) & m32, p0 & m32
+            k0, k1 = (k0 + 0x9E3779B9) & m32, (k1 + 0xBB67AE85) & m32
+        out += [c0, c1, c2, c3]
+    return np.array(out, dtype=np.uint32)
+
+
+def _reset_envs_seeded(sim: BatchedInversus, indices, seed: int) -> None:
+    """`reset(seed=s)` of the reference (env_wrappers.py:272-276 -> core.py:64-67 reseeds the env's
+    spawn generator): the new episode's spawn positions are a function of `s` only -- two envs reset
+    with the same seed start identically, whatever the runner's own seed. Implemented with the
+    C ABI's injected-draw table, so the game logic still runs in the kernel."""
+    table = np.zeros((sim.num_envs, TABLE_STRIDE), np.uint32)
+    table[:, TABLE_RESET_OFF:TABLE_RESET_OFF + 44] = _seeded_reset_draws(seed)
+    sim.set_draw_table(table)
+    try:
+        sim.reset_envs(indices)
+    finally:
+        sim.set_draw_table(None)
+
+
 class _EnvSlot:
     """`MultiEnvRunner.envs[i]`: supports what the trainer calls on it (training.py:149)."""
 
@@ -114,10 +147,11 @@ class _EnvSlot:
         self.max_episode_steps = runner.max_episode_steps
 
     def reset(self, seed: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
-        if seed is not None:
-            raise NotImplementedError("per-reset reseeding is not supported: draws are keyed by (seed, env, episode)")
         sim, i = self._runner.sim, self._index
-        sim.reset_envs([i])
+        if seed is not None:  # env_wrappers.py:272-276
+            _reset_envs_seeded(sim, [i], seed)
+        else:
+            sim.reset_envs([i])
         return sim.obs[i].float().cpu().numpy(), sim.extra[i].cpu().numpy()
 
     @property
@@ -202,8 +236,8 @@ class SingleInversusRLEnv:
         self._runner.reset()
 
     def reset(self, seed: Optional[int] = None):
-        if seed is not None:
-            raise NotImplementedError("per-reset reseeding is not supported")
+        if seed is not None:  # env_wrappers.py:272-276
+            return self._runner.envs[0].reset(seed=seed)
         g, e = self._runner.reset()
         return g[0], e[0]
 

@@ -199,3 +199,46 @@ def encode_layer1(ps: PackedStates, w1: torch.Tensor, b1: torch.Tensor, gamma_hw
     """relu(LayerNorm(conv1(observation(state)) + b1) * gamma + beta) straight from packed states:
     returns (y [M, 4800] bf16 in HWC order, extra [M, 4] f32). fp32 master weights in, fp32 grads out."""
     return _EncodeLayer1.apply(w1, b1, gamma_hwc, beta_hwc, ps, eps)
+
+
+class _Conv3x3(torch.autograd.Function):
+    """3x3 / padding-1 convolution of channels-last bf16 activations on the 15 x 10 board. Forward and
+    input gradient are the library's (cuDNN runs both at the tensor-core peak); the WEIGHT gradient,
+    where the library reaches 17 % of that peak, is the hand-written tcgen05 kernel of
+    csrc/wgrad_kernels.cu."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return torch.nn.functional.conv2d(x, w, None, padding=1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        if ctx.needs_input_grad[0]:
+            dx = torch.ops.aten.convolution_backward(dy, x, w, None, (1, 1), (1, 1), (1, 1), False, (0, 0), 1,
+                                                     (True, False, False))[0]
+        if ctx.needs_input_grad[1]:
+            B, cin = x.shape[0], x.shape[1]
+            cout = w.shape[0]
+            lib = _capi.load()
+            out = torch.empty((cout, 3, 3, cin), dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                scratch = torch.empty(lib.inv_conv3x3_wgrad_scratch_floats(cin), dtype=torch.float32, device=x.device)
+                _capi.check(lib.inv_conv3x3_wgrad(dy.data_ptr(), x.data_ptr(), B, cin, cout, out.data_ptr(),
+                                                  scratch.data_ptr(), _stream(x)))
+            dw = out.permute(0, 3, 1, 2).to(w.dtype)  # logical [co, ci, ky, kx], channels-last strides like w
+        return dx, dw
+
+
+def conv3x3_supported(x: torch.Tensor, w: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.dim() == 4
+            and tuple(x.shape[2:]) == (10, 15) and w.shape[0] == 128 and w.shape[1] in (64, 128)
+            and tuple(w.shape[2:]) == (3, 3) and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """F.conv2d(x, w, None, padding=1) with the hand-written weight gradient (conv3 / conv4 shapes)."""
+    return _Conv3x3.apply(x, w)

@@ -84,6 +84,9 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("the oracle and the live-reference harness", ""), f
+                # nor the staged copy of the reference (oracle/_ref, baseline/_ref) or the reference itself
+                assert "_ref/" not in txt and "_ref\"" not in txt and "/root/reference" not in txt, f
+                assert "import inversus_rl" not in txt and "from inversus_rl" not in txt, f
 
 
 @pytest.mark.parametrize("no_avx512", [False, True])

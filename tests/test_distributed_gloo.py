@@ -109,3 +109,60 @@ def test_gradient_all_reduce_averages_over_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+def _update_worker(rank, world, port, q):
+    """Two ranks with UNEQUAL shards (5 and 4 envs) run whole PPO updates: the bucketed gradient
+    all-reduce is driven from the backward hooks, every rank performs the same number of
+    optimisation steps, advantages are normalised with global moments, and the parameters stay
+    bit-identical across ranks."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root]
+    from inversus_b200.policies import InversusCNNPolicy
+    from inversus_b200.ppo_agent import DeviceRollout, PPOAgent
+    from inversus_b200.sharding import shard_range
+    torch.manual_seed(0)  # identical initial weights
+    agent = PPOAgent(InversusCNNPolicy(), device="cpu", epochs=2, batch_size=16)
+    _, n_local = shard_range(9, rank, world)  # 5 / 4 envs
+    T = 7                                     # 35 vs 28 samples: 3 vs 2 minibatches of 16 without the fix
+    g = torch.Generator().manual_seed(100 + rank)
+    ro = DeviceRollout(T, n_local, "cpu", store="obs")
+    steps = []
+    for _ in range(2):  # two updates
+        for t in range(T):
+            obs = (torch.rand(n_local, 12, 10, 15, generator=g) > 0.7).float()
+            extra = torch.rand(n_local, 4, generator=g)
+            a, lp, v = agent.act(obs, extra)
+            ro.store_pre((obs, extra), a, lp, v)
+            ro.store_post(torch.randn(n_local, generator=g), (torch.rand(n_local, generator=g) < 0.1).to(torch.uint8))
+        before = float(agent.optimizer.state_dict()["state"].get(0, {}).get("step", 0.0))  # a copy: the tensor is updated in place
+        agent.update(ro, None, torch.zeros(n_local))
+        steps.append(int(float(agent.optimizer.state_dict()["state"][0]["step"]) - before))
+    flat = torch.cat([p.detach().reshape(-1) for p in agent.policy.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    same = all(torch.equal(gathered[0], x) for x in gathered)
+    assert agent._flat_grad is not None and len(agent._buckets) >= 2  # the overlapped path ran
+    q.put((rank, same, steps, bool(torch.isfinite(flat).all())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_update_keeps_ranks_in_step_and_identical():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_update_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, same0, steps0, fin0), (_, same1, steps1, fin1) = res
+    assert same0 and same1 and fin0 and fin1
+    assert steps0 == steps1 == [6, 6]  # ceil(35 / 16) = 3 steps x 2 epochs on BOTH ranks
