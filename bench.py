@@ -663,9 +663,25 @@ def main():
         }
         emit(line)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        shutdown_distributed(torch, dist, dev)
     return 0
+
+
+def shutdown_distributed(torch, dist, dev):
+    """Leave a torchrun job without hanging: the PPO block replays CUDA graphs that contain NCCL
+    kernels, and tearing the communicator down while such graphs (or the watchdog's view of them)
+    are alive has been seen to block forever. Drop the graphs, synchronise, give the orderly
+    teardown 20 s on a side thread, then exit this worker with status 0."""
+    import gc
+    gc.collect()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(20.0)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -339,9 +339,22 @@ def main(argv=None):
                 reference_gae=a.reference_gae, seed=a.seed,
                 cuda_graph={"auto": None, "on": True, "off": False}[a.cuda_graph])
     if dist_env()[0] == 0:
-        print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in out.items()})
+        print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in out.items()}, flush=True)
     if torch.distributed.is_initialized():
-        torch.distributed.destroy_process_group()
+        # the update graph holds NCCL kernels: drop it, then give the communicator teardown a bounded
+        # time on a side thread (it has been seen to block with captured collectives) and leave
+        import gc
+        import sys
+        import threading
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        t = threading.Thread(target=torch.distributed.destroy_process_group, daemon=True)
+        t.start()
+        t.join(20.0)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
