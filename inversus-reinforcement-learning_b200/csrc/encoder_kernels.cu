@@ -424,10 +424,15 @@ __global__ void encode_reduce_kernel(const float *__restrict__ partials, int npa
                                      float *__restrict__ db1, float *__restrict__ dgamma, float *__restrict__ dbeta)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    auto total = [&](int off) {
-        float a = 0.f;
-        for (int p = 0; p < nparts; ++p) a += partials[(size_t)p * kPartial + off];
-        return a;
+    auto total = [&](int off) { // independent loads, eight in flight (the grid is small: latency, not bandwidth)
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int p = 0;
+        for (; p + 8 <= nparts; p += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] += partials[(size_t)(p + u) * kPartial + off];
+        }
+        for (; p < nparts; ++p) a[0] += partials[(size_t)p * kPartial + off];
+        return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     };
     if (i < kD) { dgamma[i] = total(i); return; }
     if (i < 2 * kD) { dbeta[i - kD] = total(i); return; }

@@ -658,6 +658,15 @@ int inv_step_host(inv_sim *s, const int8_t *a1, const int8_t *a2, void *obs_p1, 
     }
     if (s->h_small) nchunks = 1;
     const int64_t per = ((n + nchunks - 1) / nchunks + 255) & ~(int64_t)255;
+    // small outputs only: what is not overlapped is the LAST chunk's copy, so the chunks shrink
+    // towards the end (3 : 3 : 1 : 1)
+    int64_t bounds[kMaxHostChunks + 1];
+    const bool tapered = !(obs_p1 || obs_p2) && nchunks == 4 && !getenv("INV_HOST_CHUNKS");
+    for (int c = 0; c <= nchunks; ++c) {
+        int64_t b = tapered ? (n * (c == 0 ? 0 : c == 1 ? 3 : c == 2 ? 6 : c == 3 ? 7 : 8) / 8) & ~(int64_t)255
+                            : (int64_t)c * per;
+        bounds[c] = (c == nchunks || b > n) ? n : b;
+    }
     const SmallOut so = {extra_p1, extra_p2, reward, done, info, episode_steps, episode_return};
     const size_t env_bytes = (size_t)INV_OBS_ELEMS * obs_elem_bytes(s->cfg.obs_dtype);
     void *dst[2] = {obs_p1, obs_p2};
@@ -668,9 +677,10 @@ int inv_step_host(inv_sim *s, const int8_t *a1, const int8_t *a2, void *obs_p1, 
     // all kernels are enqueued first (the launch stream never waits for the host to issue copies) ...
     int used = 0;
     for (int c = 0; c < nchunks; ++c) {
-        const int64_t first = (int64_t)c * per;
+        const int64_t first = bounds[c];
         if (first >= n) break;
-        const int64_t count = (first + per <= n) ? per : n - first;
+        const int64_t count = bounds[c + 1] - first;
+        if (count <= 0) break;
         lo[c] = first;
         hi[c] = first + count;
         mid[c] = expand ? first + ((int64_t)((double)count * frac) & ~(int64_t)255) : first + count;

@@ -47,6 +47,48 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8])
     return v;
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on sm_100): two lanes per issue slot. The
+// LayerNorm backward is bound by instruction issue, not by HBM, so this is where its time goes.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 f2_make(float lo, float hi)
+{
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_split(f2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c)
+{
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b)
+{
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b)
+{
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// two bf16 in one 32-bit word -> two fp32
+__device__ __forceinline__ f2 bf2_to_f2(uint32_t w) { return f2_make(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)); }
+__device__ __forceinline__ uint32_t f2_to_bf2(f2 v)
+{
+    float lo, hi;
+    f2_split(v, lo, hi);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ uint32_t word_of(const uint4 &v, int p) { return p == 0 ? v.x : p == 1 ? v.y : p == 2 ? v.z : v.w; }
+
 // sum of (a, b) over the CTA; result broadcast to every thread
 __device__ __forceinline__ float2 block_sum2(float a, float b, float2 *scratch)
 {
@@ -81,8 +123,11 @@ ln_relu_fwd_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ res, c
     const int tid = threadIdx.x;
     // per-channel convolution bias, folded in here so cuDNN runs bias-free: the element (i*8 + j) of
     // an HWC sample belongs to channel ((i mod C/8)*8 + j), and since kLnThreads is a multiple of
-    // C/8 every vector of a thread sees the same 8 channels -> one register vector per thread
-    const uint4 cbv = cbias ? cbias[tid % cvecs] : make_uint4(0u, 0u, 0u, 0u); // kept packed: 4 registers
+    // C/8 every vector of a thread sees the same 8 channels -> four register pairs per thread
+    const uint4 cbv = cbias ? cbias[tid % cvecs] : make_uint4(0u, 0u, 0u, 0u);
+    f2 cb2[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) cb2[p] = bf2_to_f2(word_of(cbv, p));
     constexpr bool kCacheGB = MAXV <= 1;
     uint4 g[kCacheGB ? MAXV : 1], bt[kCacheGB ? MAXV : 1];
     if (kCacheGB) {
@@ -93,6 +138,8 @@ ln_relu_fwd_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ res, c
         }
     }
     const float inv_d = 1.0f / (float)(nvec * 8);
+    // All arithmetic is packed fp32x2 (FFMA2 / FADD2 / FMUL2): at ~10 instructions per element instead
+    // of ~17 the kernel stops being bound by instruction issue.
     for (int64_t s = blockIdx.x; s < B; s += gridDim.x) {
         const uint4 *xs = x + s * nvec;
         uint4 xv[MAXV], rv[HAS_RES ? MAXV : 1]; // inputs stay packed (bf16) between the two passes
@@ -104,57 +151,48 @@ ln_relu_fwd_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ res, c
                 if (HAS_RES) rv[k] = res[s * nvec + i];
             }
         }
-        float sum = 0.f, sq = 0.f;
+        f2 sum2 = f2_make(0.f, 0.f), sq2 = f2_make(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < MAXV; ++k) {
             const int i = k * kLnThreads + tid;
             if (i < nvec) {
-                float z[8];
-                unpack8(xv[k], z);
-                {
-                    float cb[8];
-                    unpack8(cbv, cb);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) z[j] += cb[j];
+                for (int p = 0; p < 4; ++p) {
+                    f2 z = f2_add(bf2_to_f2(word_of(xv[k], p)), cb2[p]);
+                    if (HAS_RES) z = f2_add(z, bf2_to_f2(word_of(rv[k], p)));
+                    sum2 = f2_add(sum2, z);
+                    sq2 = f2_fma(z, z, sq2);
                 }
-                if (HAS_RES) {
-                    float r[8];
-                    unpack8(rv[k], r);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) z[j] += r[j];
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { sum += z[j]; sq += z[j] * z[j]; }
             }
         }
-        const float2 t = block_sum2(sum, sq, scratch);
+        float s0, s1, q0, q1;
+        f2_split(sum2, s0, s1);
+        f2_split(sq2, q0, q1);
+        const float2 t = block_sum2(s0 + s1, q0 + q1, scratch);
         const float mean = t.x * inv_d;
         const float var = fmaxf(t.y * inv_d - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
         if (tid == 0) { mean_out[s] = mean; rstd_out[s] = rstd; }
+        const f2 rs2 = f2_make(rstd, rstd), nm2 = f2_make(-mean, -mean);
 #pragma unroll
         for (int k = 0; k < MAXV; ++k) {
             const int i = k * kLnThreads + tid;
             if (i < nvec) {
-                float z[8], gf[8], bf[8], o[8];
-                unpack8(xv[k], z);
-                {
-                    float cb[8];
-                    unpack8(cbv, cb);
+                const uint4 gk = kCacheGB ? g[k] : gamma[i], bk = kCacheGB ? bt[k] : beta[i];
+                uint32_t ow[4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) z[j] += cb[j];
+                for (int p = 0; p < 4; ++p) {
+                    f2 z = f2_add(bf2_to_f2(word_of(xv[k], p)), cb2[p]);
+                    if (HAS_RES) z = f2_add(z, bf2_to_f2(word_of(rv[k], p)));
+                    // (z - mean) * rstd * gamma + beta  =  z * (rstd*gamma) + (beta - mean*rstd*gamma)
+                    const f2 sg = f2_mul(bf2_to_f2(word_of(gk, p)), rs2);
+                    const f2 o = f2_fma(z, sg, f2_fma(sg, nm2, bf2_to_f2(word_of(bk, p))));
+                    float o0, o1;
+                    f2_split(o, o0, o1);
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(o0, 0.f), fmaxf(o1, 0.f));
+                    ow[p] = *reinterpret_cast<const uint32_t *>(&h);
                 }
-                if (HAS_RES) {
-                    float r[8];
-                    unpack8(rv[k], r);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) z[j] += r[j];
-                }
-                unpack8(kCacheGB ? g[k] : gamma[i], gf);
-                unpack8(kCacheGB ? bt[k] : beta[i], bf);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = fmaxf((z[j] - mean) * rstd * gf[j] + bf[j], 0.f);
-                y[s * nvec + i] = pack8(o);
+                y[s * nvec + i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
         }
     }
@@ -416,9 +454,9 @@ ln_relu_bwd_cluster_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict
     const uint4 gv = active ? gamma[slot] : make_uint4(0u, 0u, 0u, 0u);
     const uint4 bv = active ? beta[slot] : make_uint4(0u, 0u, 0u, 0u);
     const uint4 cbv = cbias ? cbias[tid % cvecs] : make_uint4(0u, 0u, 0u, 0u);
-    float dg[8], db[8], dcb[8];
+    f2 dg[4], db[4], dcb[4]; // column pairs (2p, 2p+1) of this thread's 8 columns
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dg[j] = db[j] = dcb[j] = 0.f;
+    for (int p = 0; p < 4; ++p) dg[p] = db[p] = dcb[p] = f2_make(0.f, 0.f);
 
     const int64_t groups = (B + S - 1) / S;
     const int G = cid < groups ? (int)((groups - cid + nclusters - 1) / nclusters) : 0; // same in every CTA of the cluster
@@ -466,30 +504,34 @@ ln_relu_bwd_cluster_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict
                 const int64_t smp = grp * S + k;
                 if (active && smp < B) {
                     const float rs = rstd_in[smp], nmr = -mean_in[smp] * rs;
-                    float z[8], d[8], cb[8], g[8], bt[8];
-                    unpack8(stage_ptr(stage, k, 0)[tid], z);
-                    unpack8(stage_ptr(stage, k, 1)[tid], d);
-                    unpack8(cbv, cb);
-                    unpack8(gv, g);
-                    unpack8(bv, bt);
-                    if (HAS_RES) {
-                        float r[8];
-                        unpack8(stage_ptr(stage, k, 2)[tid], r);
+                    const f2 rs2 = f2_make(rs, rs), nmr2 = f2_make(nmr, nmr);
+                    const uint4 xv = stage_ptr(stage, k, 0)[tid], dv = stage_ptr(stage, k, 1)[tid];
+                    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+                    if (HAS_RES) rv = stage_ptr(stage, k, 2)[tid];
+                    f2 s1 = f2_make(0.f, 0.f), s2 = f2_make(0.f, 0.f);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) z[j] += r[j];
+                    for (int p = 0; p < 4; ++p) {
+                        f2 z = f2_add(bf2_to_f2(word_of(xv, p)), bf2_to_f2(word_of(cbv, p)));
+                        if (HAS_RES) z = f2_add(z, bf2_to_f2(word_of(rv, p)));
+                        const f2 g2 = bf2_to_f2(word_of(gv, p));
+                        const f2 hh = f2_fma(z, rs2, nmr2);
+                        float pre0, pre1;
+                        f2_split(f2_fma(hh, g2, bf2_to_f2(word_of(bv, p))), pre0, pre1);
+                        const uint32_t dw = word_of(dv, p);
+                        const bool on0 = pre0 > 0.f, on1 = pre1 > 0.f; // relu'
+                        const f2 gy = f2_make(on0 ? __uint_as_float(dw << 16) : 0.f, on1 ? __uint_as_float(dw & 0xFFFF0000u) : 0.f);
+                        mask_cur[k] |= (on0 ? 1u : 0u) << (2 * p) | (on1 ? 2u : 0u) << (2 * p);
+                        dg[p] = f2_fma(gy, hh, dg[p]);
+                        db[p] = f2_add(db[p], gy);
+                        const f2 ww = f2_mul(gy, g2);
+                        s1 = f2_add(s1, ww);
+                        s2 = f2_fma(ww, hh, s2);
                     }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float hh = (z[j] + cb[j]) * rs + nmr;
-                        const bool on = hh * g[j] + bt[j] > 0.f; // relu'
-                        const float gy = on ? d[j] : 0.f;
-                        mask_cur[k] |= on ? (1u << j) : 0u;
-                        dg[j] += gy * hh;
-                        db[j] += gy;
-                        const float ww = gy * g[j];
-                        p1[k] += ww;
-                        p2[k] += ww * hh;
-                    }
+                    float a0, a1, b0, b1;
+                    f2_split(s1, a0, a1);
+                    f2_split(s2, b0, b1);
+                    p1[k] = a0 + a1;
+                    p2[k] = b0 + b1;
                 }
             }
 #pragma unroll
@@ -534,26 +576,26 @@ ln_relu_bwd_cluster_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict
                 const int64_t smp = grp * S + k;
                 if (active && smp < B) {
                     const float rs = rstd_in[smp], nmr = -mean_in[smp] * rs;
-                    const float a = t1 * inv_d * rs, b = t2 * inv_d * rs; // m1 * rstd, m2 * rstd
-                    float z[8], d[8], cb[8], g[8], o[8];
-                    unpack8(stage_ptr(stage, k, 0)[tid], z);
-                    unpack8(stage_ptr(stage, k, 1)[tid], d);
-                    unpack8(cbv, cb);
-                    unpack8(gv, g);
-                    if (HAS_RES) {
-                        float r[8];
-                        unpack8(stage_ptr(stage, k, 2)[tid], r);
+                    const float a = -(t1 * inv_d * rs), b = -(t2 * inv_d * rs); // -m1 * rstd, -m2 * rstd
+                    const f2 rs2 = f2_make(rs, rs), nmr2 = f2_make(nmr, nmr), a2 = f2_make(a, a), b2 = f2_make(b, b);
+                    const uint4 xv = stage_ptr(stage, k, 0)[tid], dv = stage_ptr(stage, k, 1)[tid];
+                    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+                    if (HAS_RES) rv = stage_ptr(stage, k, 2)[tid];
+                    uint32_t ow[4];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) z[j] += r[j];
+                    for (int p = 0; p < 4; ++p) {
+                        f2 z = f2_add(bf2_to_f2(word_of(xv, p)), bf2_to_f2(word_of(cbv, p)));
+                        if (HAS_RES) z = f2_add(z, bf2_to_f2(word_of(rv, p)));
+                        const f2 hh = f2_fma(z, rs2, nmr2);
+                        const uint32_t dw = word_of(dv, p), mk = mask_prev[k] >> (2 * p);
+                        const f2 gy = f2_make((mk & 1u) ? __uint_as_float(dw << 16) : 0.f,
+                                              (mk & 2u) ? __uint_as_float(dw & 0xFFFF0000u) : 0.f);
+                        const f2 ww = f2_mul(gy, bf2_to_f2(word_of(gv, p)));
+                        const f2 o = f2_fma(hh, b2, f2_fma(ww, rs2, a2)); // w*rstd - m1*rstd - h*m2*rstd
+                        dcb[p] = f2_add(dcb[p], o);
+                        ow[p] = f2_to_bf2(o);
                     }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float hh = (z[j] + cb[j]) * rs + nmr;
-                        const float ww = ((mask_prev[k] >> j) & 1u) ? d[j] * g[j] : 0.f;
-                        o[j] = ww * rs - a - hh * b;
-                        dcb[j] += o[j];
-                    }
-                    dx[smp * nvec + slot] = pack8(o);
+                    dx[smp * nvec + slot] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }
             }
         }
@@ -566,14 +608,14 @@ ln_relu_bwd_cluster_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict
     if (active) {
         float *out = partials + (size_t)cid * 2 * D + (size_t)slot * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            out[j] = dg[j];
-            out[D + j] = db[j];
+        for (int p = 0; p < 4; ++p) {
+            f2_split(dg[p], out[2 * p], out[2 * p + 1]);
+            f2_split(db[p], out[D + 2 * p], out[D + 2 * p + 1]);
         }
     }
     // d(conv bias): fold the threads that share a channel group (tid % cvecs) through shared memory
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s_cb[tid * 8 + j] = dcb[j];
+    for (int p = 0; p < 4; ++p) f2_split(dcb[p], s_cb[tid * 8 + 2 * p], s_cb[tid * 8 + 2 * p + 1]);
     __syncthreads();
     const int C = cvecs * 8;
     if (tid < C) {
@@ -594,12 +636,14 @@ __global__ void reduce_cluster_partials_kernel(const float *__restrict__ partial
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 2 * D) {
         float s = 0.f;
+#pragma unroll 8
         for (int p = 0; p < nclusters; ++p) s += partials[(size_t)p * 2 * D + i];
         if (i < D) dgamma[i] = s;
         else dbeta[i - D] = s;
     } else if (i < 2 * D + C && dcbias) {
         const float *cbp = partials + (size_t)nclusters * 2 * D;
         float s = 0.f;
+#pragma unroll 8
         for (int p = 0; p < nctas; ++p) s += cbp[(size_t)p * C + (i - 2 * D)];
         dcbias[i - 2 * D] = s;
     }
@@ -749,11 +793,12 @@ int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *
     if (!dy || !x || !gamma || !beta || !mean || !rstd || !dx || !dgamma || !dbeta || !partials || B <= 0 ||
         D <= 0 || D % 8)
         return INV_ERR_INVALID_ARG;
-    {   // INV_LN_BWD=cluster selects the cluster-split kernel (experiments); default: one CTA per SM
+    {   // default: the cluster-split kernel; INV_LN_BWD=percta selects the round-1 kernel (one CTA per
+        // SM, shared-memory accumulators) for A/B measurements
         static int use_cluster = -1;
         if (use_cluster < 0) {
             const char *e = getenv("INV_LN_BWD");
-            use_cluster = (e && e[0] == 'c') ? 1 : 0;
+            use_cluster = (e && e[0] == 'p') ? 0 : 1;
         }
         if (!use_cluster)
             return ln_relu_bwd_percta(dy, x, res, cbias, gamma, beta, mean, rstd, B, D, C, dx, dgamma, dbeta, dcbias,

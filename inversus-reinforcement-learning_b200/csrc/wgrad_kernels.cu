@@ -218,6 +218,7 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ partials, int part
     if (i >= total) return;
     const int ci = i % cin, co = (i / cin) % kCout, tap = i / (cin * kCout);
     float a = 0.f;
+#pragma unroll 8
     for (int p = 0; p < parts; ++p) a += partials[(size_t)p * total + i];
     dw[((size_t)co * 9 + tap) * cin + ci] = a;
 }
