@@ -503,6 +503,21 @@ def main():
     total_ms_max = float(t.item())
     value = n * world * args.steps / (total_ms_max * 1e-3)
 
+    # write-only ceiling of this GPU, measured live: the step kernel is 99 % stores, and a pure store
+    # stream runs above the copy figure that MEASURED_PEAKS.json holds (no read/write turnaround)
+    fill = torch.empty(1 << 30, dtype=torch.float32, device=dev)  # 4 GiB
+    for _ in range(2):
+        fill.zero_()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(5):
+        fill.zero_()
+    f1.record()
+    torch.cuda.synchronize()
+    fill_gbs = 5 * fill.numel() * 4 / (f0.elapsed_time(f1) * 1e-3) / 1e9
+    del fill
+    torch.cuda.empty_cache()
+
     elem = {"f32": 4, "bf16": 2, "u8": 1}[args.obs_dtype]
     alg_bytes = constants.algorithmic_bytes_per_env_step(elem, selfplay) * n
     avg_launch_ms = sum(per_launch_ms) / len(per_launch_ms)
@@ -511,6 +526,8 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(args.obs_dtype, args.mode, n),
                 "kernel": "inv::inv_kernel<OP_STEP> (fused step+obs)", "peak_source": peak_src,
+                "write_only_ceiling_gbs": fill_gbs, "frac_of_write_only_ceiling": achieved / fill_gbs,
+                "write_only_ceiling_source": "cudaMemset of 4 GiB timed in this run (the kernel's traffic is 99 % stores)",
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "algorithmic_bytes_per_env_step": alg_bytes // n,
                 "avg_launch_ms": avg_launch_ms, "min_launch_ms": min(per_launch_ms),
