@@ -160,6 +160,18 @@ constexpr int kTileEnvs = 32;
 // more store warps per CTA lift the step kernel from 6.39 to 6.93 TB/s (a pure store stream in
 // the same shape reaches 7.1-7.5 TB/s, profiles/r2_store_ceiling.txt). Small batches keep the
 // 32-env / 128-thread shape (more CTAs, shorter critical path).
+#ifndef INV_BF16_E   // bf16 one-view step: tile envs / threads per CTA
+#define INV_BF16_E 64
+#endif
+#ifndef INV_BF16_T
+#define INV_BF16_T 128
+#endif
+#ifndef INV_NARROW_E // u8 and two-view bf16 steps
+#define INV_NARROW_E 128
+#endif
+#ifndef INV_NARROW_T
+#define INV_NARROW_T 128
+#endif
 #ifndef INV_WIDE_MIN_ENVS
 #define INV_WIDE_MIN_ENVS 131072
 #endif
@@ -191,8 +203,9 @@ cudaError_t launch_e(const Params &p, int sm_count, cudaStream_t st)
     if constexpr (DT == INV_OBS_NONE && !INDEXED && OP != OP_DEBUG) {
         return launch_one<OP, DT, P2V, false, 128, 128>(p, sm_count, st); // pure thread-per-env, no store phase
     } else if constexpr (OP == OP_STEP && !INDEXED && DT != INV_OBS_F32) {
-        constexpr int E = (DT == INV_OBS_BF16 && !P2V) ? 64 : 128;
-        return launch_one<OP_STEP, DT, P2V, false, E>(p, sm_count, st);
+        constexpr int E = (DT == INV_OBS_BF16 && !P2V) ? INV_BF16_E : INV_NARROW_E;
+        constexpr int T = (DT == INV_OBS_BF16 && !P2V) ? INV_BF16_T : INV_NARROW_T;
+        return launch_one<OP_STEP, DT, P2V, false, E, T>(p, sm_count, st);
     } else if constexpr (DT == INV_OBS_F32 && !INDEXED && OP != OP_DEBUG) {
         if (p.count >= INV_WIDE_MIN_ENVS) {
             if constexpr (OP == OP_STEP && !P2V) return launch_one<OP, DT, P2V, false, 64, 256>(p, sm_count, st);
