@@ -66,6 +66,8 @@ typedef enum { INV_OBS_F32 = 0, INV_OBS_BF16 = 1, INV_OBS_U8 = 2, INV_OBS_NONE =
 /* inv_config.flags */
 #define INV_FLAG_AUTO_RESET 1u /* fuse the trainer's reset-on-done (training.py:140-151) into step */
 #define INV_FLAG_P2_VIEW 2u    /* also emit the P2-perspective observation (selfplay, env_wrappers.py:311) */
+#define INV_FLAG_REWARD_F64 4u /* also keep the step reward as the binary64 sum the reference returns from
+                                  SingleInversusRLEnv.step (env_wrappers.py:343-444), before its float32 cast */
 
 /* bits of the per-env info byte (env_wrappers.py:360-427) */
 #define INV_INFO_LANDED_HIT 1u
@@ -117,7 +119,8 @@ typedef enum {
     INV_BUF_EPISODE_STEPS = 7,  /* [n] i32 -- info["episode_steps"], env_wrappers.py:441 */
     INV_BUF_EPISODE_RETURN = 8, /* [n] f64 -- info["episode_return"], env_wrappers.py:442 */
     INV_BUF_PACKED_STATE = 9,   /* [5,n] uint4 planes, INV_PACKED_STATE_BYTES per env */
-    INV_BUF_DEBUG_RESULT = 10   /* [n] u8 -- return value of the last inv_debug_phase call */
+    INV_BUF_DEBUG_RESULT = 10,  /* [n] u8 -- return value of the last inv_debug_phase call */
+    INV_BUF_REWARD_F64 = 11     /* [n] f64 -- the unrounded reward (INV_FLAG_REWARD_F64) */
 } inv_buffer;
 
 /* engine calls reachable one at a time through inv_debug_phase (parity tests only) */

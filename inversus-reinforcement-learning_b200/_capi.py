@@ -17,9 +17,9 @@ ERR_INVALID_ARG, ERR_CUDA, ERR_INVALID_ACTION, ERR_BULLET_OVERFLOW, ERR_NOT_RESE
 MODE = {"dummy": 0, "selfplay": 1}
 DIFFICULTY = {"easy": 0, "hard": 1}
 OBS_DTYPE = {"f32": 0, "float32": 0, "bf16": 1, "bfloat16": 1, "u8": 2, "uint8": 2, "none": 3}
-FLAG_AUTO_RESET, FLAG_P2_VIEW = 1, 2
+FLAG_AUTO_RESET, FLAG_P2_VIEW, FLAG_REWARD_F64 = 1, 2, 4
 (BUF_OBS_P1, BUF_EXTRA_P1, BUF_OBS_P2, BUF_EXTRA_P2, BUF_REWARD, BUF_DONE, BUF_INFO,
- BUF_EPISODE_STEPS, BUF_EPISODE_RETURN, BUF_PACKED_STATE, BUF_DEBUG_RESULT) = range(11)
+ BUF_EPISODE_STEPS, BUF_EPISODE_RETURN, BUF_PACKED_STATE, BUF_DEBUG_RESULT, BUF_REWARD_F64) = range(12)
 (PHASE_TRY_MOVE, PHASE_SPAWN_BULLET, PHASE_WIDE_SHOT, PHASE_RELOAD, PHASE_UPDATE_BULLETS,
  PHASE_STEP_PLAYERS, PHASE_ENGINE_RESET, PHASE_DUMMY_POLICY) = range(8)
 

@@ -29,7 +29,7 @@ struct inv_sim {
     float *extra1, *extra2, *reward;
     uint8_t *done, *info, *dbg;
     int32_t *ep_steps;
-    double *ep_return;
+    double *ep_return, *reward64;
     uint32_t *status;
     const uint32_t *table;
     int sm_count;
@@ -135,7 +135,7 @@ Params base_params(const inv_sim *s)
     p.obs1 = s->obs1; p.obs2 = s->obs2;
     p.bits1 = nullptr; p.bits2 = nullptr;
     p.extra1 = s->extra1; p.extra2 = s->extra2;
-    p.reward = s->reward; p.done = s->done; p.info = s->info; p.dbg = s->dbg;
+    p.reward = s->reward; p.reward64 = s->reward64; p.done = s->done; p.info = s->info; p.dbg = s->dbg;
     p.ep_steps = s->ep_steps; p.ep_return = s->ep_return;
     p.status = s->status;
     p.seed_lo = (uint32_t)s->cfg.seed;
@@ -381,6 +381,7 @@ int inv_create(const inv_config *cfg, inv_sim **out)
         s->info = reinterpret_cast<uint8_t *>(s->d_small + s->off_info);
     }
     ALLOC(s->dbg, (size_t)n);
+    if (cfg->flags & INV_FLAG_REWARD_F64) ALLOC(s->reward64, (size_t)n * 8);
     ALLOC(s->status, 4);
     ALLOC(s->d_a1, (size_t)n);
     ALLOC(s->d_a2, (size_t)n);
@@ -419,7 +420,7 @@ int inv_destroy(inv_sim *s)
     if (!s) return INV_OK;
     DeviceGuard g(s->cfg.device);
     cudaDeviceSynchronize();
-    void *dev[] = {s->state, s->obs1, s->obs2, s->d_small, s->dbg, s->status, s->d_a1, s->d_a2};
+    void *dev[] = {s->state, s->obs1, s->obs2, s->d_small, s->dbg, s->status, s->d_a1, s->d_a2, s->reward64};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (s->h_small) cudaFreeHost(s->h_small);
@@ -492,6 +493,7 @@ static Params chunk_params(const Params &b, int64_t first, int64_t count, size_t
     p.extra1 = b.extra1 + first * 4;
     if (b.extra2) p.extra2 = b.extra2 + first * 4;
     p.reward = b.reward + first;
+    if (b.reward64) p.reward64 = b.reward64 + first;
     p.done = b.done + first;
     p.info = b.info + first;
     p.dbg = b.dbg + first;
@@ -827,6 +829,7 @@ int inv_get_buffer(inv_sim *s, int which, void **dev_ptr, int64_t *nbytes)
     case INV_BUF_EPISODE_RETURN: p = s->ep_return; b = n * 8; break;
     case INV_BUF_PACKED_STATE: p = s->state; b = n * INV_PACKED_STATE_BYTES; break;
     case INV_BUF_DEBUG_RESULT: p = s->dbg; b = n; break;
+    case INV_BUF_REWARD_F64: p = s->reward64; b = s->reward64 ? n * 8 : 0; break;
     default: return fail(INV_ERR_INVALID_ARG, "inv_get_buffer: unknown buffer id");
     }
     if (!p) return fail(INV_ERR_INVALID_ARG, "inv_get_buffer: buffer not allocated for this configuration");

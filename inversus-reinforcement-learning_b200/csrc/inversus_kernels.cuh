@@ -77,6 +77,7 @@ struct Params {
     uint4 *bits1, *bits2;    // optional: packed observation rows, 16 x 16 B per env (host-expand path)
     float *extra1, *extra2;
     float *reward;
+    double *reward64;        // optional: the unrounded binary64 reward (INV_FLAG_REWARD_F64)
     uint8_t *done, *info, *dbg;
     int32_t *ep_steps;
     double *ep_return;
@@ -500,6 +501,7 @@ __device__ __forceinline__ void build_row(uint32_t *row, const Env &s, const uin
 
 struct StepResult {
     float reward;      // env_wrappers.py:525 (binary64 sum rounded to float32)
+    double reward64;   // the sum itself (what SingleInversusRLEnv.step returns, env_wrappers.py:444)
     uint8_t done, info;
     int32_t ep_steps;  // info["episode_steps"], before any auto-reset
     double ep_return;  // info["episode_return"]
@@ -575,6 +577,7 @@ __device__ __forceinline__ StepResult rl_step(Env &s, uint16_t *sb, int a1, int 
     s.ret = __dadd_rn(s.ret, r);                                                            // :440
     StepResult o;
     o.reward = __double2float_rn(r);
+    o.reward64 = r;
     o.done = done ? 1 : 0;
     o.info = (uint8_t)info;
     o.ep_steps = (int32_t)s.step;
@@ -709,6 +712,7 @@ __global__ void __launch_bounds__(T) inv_kernel(const Params p)
             if (OP == OP_STEP) {
                 const StepResult o = rl_step<E>(s, sb, p.a1[ei], p.mode == INV_MODE_DUMMY ? 0 : p.a2[ei], p, gid, trow);
                 p.reward[ei] = o.reward;                                                           // env_wrappers.py:525
+                if (p.reward64) p.reward64[ei] = o.reward64;
                 p.done[ei] = o.done;
                 p.info[ei] = o.info;
                 p.ep_steps[ei] = o.ep_steps;

@@ -164,13 +164,14 @@ class MultiEnvRunner:
     reference, finished envs are reset by the caller through `envs[i].reset()`."""
 
     def __init__(self, num_envs: int, opponent_type: str = "dummy", difficulty: str = "easy",
-                 max_episode_steps: int = 500, seed: Optional[int] = None, *, device=0, env_id_base: int = 0):
+                 max_episode_steps: int = 500, seed: Optional[int] = None, *, device=0, env_id_base: int = 0,
+                 reward_f64: bool = False):
         self.num_envs = num_envs
         self.opponent_type = opponent_type
         self.difficulty = difficulty
         self.max_episode_steps = max_episode_steps
         self.sim = BatchedInversus(num_envs, opponent_type, difficulty, max_episode_steps, seed, device=device,
-                                   obs_dtype="f32", auto_reset=False, env_id_base=env_id_base)
+                                   obs_dtype="f32", auto_reset=False, env_id_base=env_id_base, reward_f64=reward_f64)
         self.envs = [_EnvSlot(self, i) for i in range(num_envs)]
         self.episode_returns = [0.0] * num_envs
         self.episode_lengths = [0] * num_envs
@@ -230,7 +231,8 @@ class SingleInversusRLEnv:
 
     def __init__(self, opponent_type: str = "dummy", difficulty: str = "easy", max_episode_steps: int = 500,
                  seed: Optional[int] = None, *, device=0):
-        self._runner = MultiEnvRunner(1, opponent_type, difficulty, max_episode_steps, seed, device=device)
+        self._runner = MultiEnvRunner(1, opponent_type, difficulty, max_episode_steps, seed, device=device,
+                                      reward_f64=True)
         self.opponent_type, self.difficulty, self.max_episode_steps = opponent_type, difficulty, max_episode_steps
         self.env = self._runner.envs[0].env
         self._runner.reset()
@@ -242,8 +244,10 @@ class SingleInversusRLEnv:
         return g[0], e[0]
 
     def step(self, action_id: int, opponent_policy=None):
-        (g, e), r, d, infos = self._runner.step(np.array([action_id]), opponent_policy)
-        return (g[0], e[0]), float(r[0]), bool(d[0]), infos[0]
+        (g, e), _, d, infos = self._runner.step(np.array([action_id]), opponent_policy)
+        # the reference returns the binary64 reward here (env_wrappers.py:444); only MultiEnvRunner
+        # casts to float32 (env_wrappers.py:525)
+        return (g[0], e[0]), float(self._runner.sim.reward_f64[0]), bool(d[0]), infos[0]
 
     @property
     def step_count(self) -> int:

@@ -69,7 +69,7 @@ class BatchedInversus:
     def __init__(self, num_envs: int, opponent_type: str = "dummy", difficulty: str = "easy",
                  max_episode_steps: int = 500, seed: Optional[int] = None, *, device=0,
                  obs_dtype: str = "f32", auto_reset: bool = True, env_id_base: int = 0,
-                 p2_view: Optional[bool] = None):
+                 p2_view: Optional[bool] = None, reward_f64: bool = False):
         if opponent_type not in _capi.MODE:
             raise ValueError(f"Unknown opponent_type: {opponent_type}")  # env_wrappers.py:316
         if difficulty not in _capi.DIFFICULTY:
@@ -89,6 +89,8 @@ class BatchedInversus:
         flags = (_capi.FLAG_AUTO_RESET if auto_reset else 0)
         if p2_view or (p2_view is None and opponent_type == "selfplay"):
             flags |= _capi.FLAG_P2_VIEW
+        if reward_f64:  # also keep the unrounded binary64 reward (what SingleInversusRLEnv.step returns)
+            flags |= _capi.FLAG_REWARD_F64
         self._dt = _capi.OBS_DTYPE[obs_dtype]
         cfg = _capi.Config(self.num_envs, self.env_id_base, self.seed, _capi.MODE[opponent_type],
                            _capi.DIFFICULTY[difficulty], self.max_episode_steps, self.device.index,
@@ -108,6 +110,7 @@ class BatchedInversus:
         self.info = self._view(_capi.BUF_INFO, (n,), "|u1")
         self.episode_steps = self._view(_capi.BUF_EPISODE_STEPS, (n,), "<i4")
         self.episode_return = self._view(_capi.BUF_EPISODE_RETURN, (n,), "<f8")
+        self.reward_f64 = self._view(_capi.BUF_REWARD_F64, (n,), "<f8") if reward_f64 else None
         self.packed_state = self._view(_capi.BUF_PACKED_STATE, (5, n, 4), "<i4")
         self.debug_result = self._view(_capi.BUF_DEBUG_RESULT, (n,), "|u1")
         self._table = None

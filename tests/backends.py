@@ -63,7 +63,7 @@ class CudaBackend:
         self.selfplay = sc["mode"] == "selfplay"
         self.sim = BatchedInversus(n or sc["n"], sc["mode"], sc["difficulty"], sc["max_steps"], seed=sc["seed"],
                                    auto_reset=(sc["resets"] == "auto"), env_id_base=env_id_base,
-                                   obs_dtype=obs_dtype, p2_view=True)
+                                   obs_dtype=obs_dtype, p2_view=True, reward_f64=True)
 
     def _table(self, table):
         self.sim.set_draw_table(table)
@@ -78,7 +78,9 @@ class CudaBackend:
         s = self.sim
         s.step(self.torch.from_numpy(np.asarray(a1, np.int8)).cuda(),
                None if a2 is None else self.torch.from_numpy(np.asarray(a2, np.int8)).cuda())
-        out = dict(reward=s.reward.cpu().numpy(), done=s.done.cpu().numpy(), flags=s.info.cpu().numpy(),
+        r64 = s.reward_f64.cpu().numpy()  # the unrounded binary64 reward; the f32 output must be its rounding
+        assert np.array_equal(s.reward.cpu().numpy(), r64.astype(np.float32))
+        out = dict(reward=r64, done=s.done.cpu().numpy(), flags=s.info.cpu().numpy(),
                    episode_steps=s.episode_steps.cpu().numpy(), episode_return=s.episode_return.cpu().numpy(),
                    obs1=s.obs.float().cpu().numpy(), extra1=s.extra.cpu().numpy())
         if self.selfplay:

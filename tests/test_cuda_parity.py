@@ -24,6 +24,7 @@ def test_cuda_reproduces_reference_fixture(name):
     rec = run_scenario(CudaBackend(sc), sc)
     compare(rec, gold, float_rtol=1e-6, what=name)
     assert np.array_equal(rec["reward_f32"], gold["reward_f32"])
+    assert np.array_equal(rec["reward"], gold["reward"])  # the binary64 reward of the reference, bit for bit
     assert np.array_equal(rec["episode_return"], gold["episode_return"])
 
 
