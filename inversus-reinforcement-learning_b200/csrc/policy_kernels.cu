@@ -402,20 +402,20 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, ui
 // tid` owns columns [8*slot, 8*slot + 8) of every sample: gamma/beta/conv-bias and the three
 // gradient accumulators of those columns are registers for the whole kernel.
 //
-// Software pipeline, one group deep. Iteration i runs
-//   pass 1 of group i    row sums s1, s2 + dgamma/dbeta accumulation; the CTA's partial sums go to
-//                        every CTA of the cluster with st.async into distributed shared memory,
-//                        counted by the receiver's mbarrier (no cluster barrier, no fence);
-//   pass 2 of group i-1  whose cluster-wide sums have had a whole pass to arrive: dx and d(bias).
-// The inputs of a group (x, dy, residual slices of S samples) are brought in by TMA bulk copies
-// into a 3-stage shared-memory ring, two groups ahead of their use, so both passes read shared
-// memory and HBM streams continuously. Pass 2 recomputes h and w from the ring instead of holding
-// them in registers (96 registers per thread => two CTAs per SM).
+// Per group of S samples:
+//   pass 1   reads the group's x / dy / residual slices from shared memory, where TMA bulk copies put
+//            them one to two groups ahead (2-stage ring), forms h and w = relu'(.) * dy * gamma --
+//            kept in registers -- accumulates dgamma / dbeta and the CTA's share of the row sums;
+//   exchange the 2*S sums go to every CTA of the cluster with st.async into distributed shared
+//            memory, counted by the receiver's mbarrier (no cluster barrier, no fence in the loop);
+//            the other CTA resident on the SM works while this one waits;
+//   pass 2   dx = rstd * (w - m1 - h * m2) from the registers, d(bias) accumulation, 16-byte stores.
+// All arithmetic is packed fp32x2. One __syncthreads per group.
 // partials layout (floats): [nclusters][2][D] (dgamma, dbeta) followed by [grid][C] (d conv bias).
 constexpr int kBwdThreads = 320;
 constexpr int kMaxCluster = 8;
-constexpr int kBwdStages = 3;
-constexpr int kSumSlots = 4; // a peer can run up to two groups ahead of the slowest reader (see below)
+constexpr int kBwdStages = 2;
+constexpr int kSumSlots = 2; // a peer is at most one group ahead of the slowest reader (see below)
 
 template <int S, bool HAS_RES>
 constexpr size_t bwd_cluster_smem() { return (size_t)kBwdStages * S * (HAS_RES ? 3 : 2) * kBwdThreads * 16; }
@@ -487,122 +487,106 @@ ln_relu_bwd_cluster_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict
         if (G > 1) issue(1);
     }
     const uint32_t sum_bytes = (uint32_t)(2 * S * cs * sizeof(float));
-    uint32_t mask_cur[S], mask_prev[S]; // relu' bits of this thread's 8 columns, per sample of the group
-#pragma unroll
-    for (int k = 0; k < S; ++k) mask_cur[k] = mask_prev[k] = 0u;
 
-    for (int i = 0; i <= G; ++i) {
-        if (i < G) { // ---------------------------------------------------------------- pass 1, group i
-            const int64_t grp = cid + (int64_t)i * nclusters;
-            const int stage = i % kBwdStages;
-            mbar_wait(smem_u32(&s_full[stage]), (uint32_t)(i / kBwdStages) & 1u);
-            float p1[S], p2[S];
+    for (int i = 0; i < G; ++i) {
+        const int64_t grp = cid + (int64_t)i * nclusters;
+        const int stage = i % kBwdStages, q = i % kSumSlots;
+        mbar_wait(smem_u32(&s_full[stage]), (uint32_t)(i / kBwdStages) & 1u);
+        // ---------------------------------------------------------------- pass 1
+        f2 h[S][4], w[S][4];
+        float p1[S], p2[S], rs[S];
 #pragma unroll
-            for (int k = 0; k < S; ++k) {
-                p1[k] = p2[k] = 0.f;
-                mask_cur[k] = 0u;
-                const int64_t smp = grp * S + k;
-                if (active && smp < B) {
-                    const float rs = rstd_in[smp], nmr = -mean_in[smp] * rs;
-                    const f2 rs2 = f2_make(rs, rs), nmr2 = f2_make(nmr, nmr);
-                    const uint4 xv = stage_ptr(stage, k, 0)[tid], dv = stage_ptr(stage, k, 1)[tid];
-                    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
-                    if (HAS_RES) rv = stage_ptr(stage, k, 2)[tid];
-                    f2 s1 = f2_make(0.f, 0.f), s2 = f2_make(0.f, 0.f);
+        for (int k = 0; k < S; ++k) {
+            p1[k] = p2[k] = rs[k] = 0.f;
+            const int64_t smp = grp * S + k;
+            if (active && smp < B) {
+                rs[k] = rstd_in[smp];
+                const float nmr = -mean_in[smp] * rs[k];
+                const f2 rs2 = f2_make(rs[k], rs[k]), nmr2 = f2_make(nmr, nmr);
+                const uint4 xv = stage_ptr(stage, k, 0)[tid], dv = stage_ptr(stage, k, 1)[tid];
+                uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+                if (HAS_RES) rv = stage_ptr(stage, k, 2)[tid];
+                f2 s1 = f2_make(0.f, 0.f), s2 = f2_make(0.f, 0.f);
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        f2 z = f2_add(bf2_to_f2(word_of(xv, p)), bf2_to_f2(word_of(cbv, p)));
-                        if (HAS_RES) z = f2_add(z, bf2_to_f2(word_of(rv, p)));
-                        const f2 g2 = bf2_to_f2(word_of(gv, p));
-                        const f2 hh = f2_fma(z, rs2, nmr2);
-                        float pre0, pre1;
-                        f2_split(f2_fma(hh, g2, bf2_to_f2(word_of(bv, p))), pre0, pre1);
-                        const uint32_t dw = word_of(dv, p);
-                        const bool on0 = pre0 > 0.f, on1 = pre1 > 0.f; // relu'
-                        const f2 gy = f2_make(on0 ? __uint_as_float(dw << 16) : 0.f, on1 ? __uint_as_float(dw & 0xFFFF0000u) : 0.f);
-                        mask_cur[k] |= (on0 ? 1u : 0u) << (2 * p) | (on1 ? 2u : 0u) << (2 * p);
-                        dg[p] = f2_fma(gy, hh, dg[p]);
-                        db[p] = f2_add(db[p], gy);
-                        const f2 ww = f2_mul(gy, g2);
-                        s1 = f2_add(s1, ww);
-                        s2 = f2_fma(ww, hh, s2);
-                    }
-                    float a0, a1, b0, b1;
-                    f2_split(s1, a0, a1);
-                    f2_split(s2, b0, b1);
-                    p1[k] = a0 + a1;
-                    p2[k] = b0 + b1;
+                for (int p = 0; p < 4; ++p) {
+                    f2 z = f2_add(bf2_to_f2(word_of(xv, p)), bf2_to_f2(word_of(cbv, p)));
+                    if (HAS_RES) z = f2_add(z, bf2_to_f2(word_of(rv, p)));
+                    const f2 g2 = bf2_to_f2(word_of(gv, p));
+                    const f2 hh = f2_fma(z, rs2, nmr2);
+                    float pre0, pre1;
+                    f2_split(f2_fma(hh, g2, bf2_to_f2(word_of(bv, p))), pre0, pre1);
+                    const uint32_t dw = word_of(dv, p);
+                    const f2 gy = f2_make(pre0 > 0.f ? __uint_as_float(dw << 16) : 0.f,      // relu'
+                                          pre1 > 0.f ? __uint_as_float(dw & 0xFFFF0000u) : 0.f);
+                    dg[p] = f2_fma(gy, hh, dg[p]);
+                    db[p] = f2_add(db[p], gy);
+                    const f2 ww = f2_mul(gy, g2);
+                    h[k][p] = hh;
+                    w[k][p] = ww;
+                    s1 = f2_add(s1, ww);
+                    s2 = f2_fma(ww, hh, s2);
                 }
-            }
+                float a0, a1, b0, b1;
+                f2_split(s1, a0, a1);
+                f2_split(s2, b0, b1);
+                p1[k] = a0 + a1;
+                p2[k] = b0 + b1;
+            } else {
 #pragma unroll
-            for (int k = 0; k < S; ++k) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    p1[k] += __shfl_xor_sync(0xffffffffu, p1[k], o);
-                    p2[k] += __shfl_xor_sync(0xffffffffu, p2[k], o);
-                }
-                if (lane == 0) {
-                    s_warp[warp][2 * k] = p1[k];
-                    s_warp[warp][2 * k + 1] = p2[k];
-                }
-            }
-            __syncthreads();
-            // This CTA's 2*S sums go to every CTA of the cluster (itself included). The receiver's
-            // mbarrier counts the bytes. Slot = i mod 4: a peer may already be sending group i+2
-            // while the slowest CTA still reads group i-1 (it cannot pass pass-2 of group i+1
-            // without that CTA's sums of i+1, which are sent after its pass-2 of i-1).
-            const int q = i % kSumSlots;
-            const uint32_t bar = smem_u32(&s_sum[q]);
-            if (tid == 0) mbar_expect_tx(bar, sum_bytes);
-            for (int e = tid; e < 2 * S * (int)cs; e += kBwdThreads) {
-                const int v = e % (2 * S), dst = e / (2 * S);
-                float a = 0.f;
-#pragma unroll
-                for (int w = 0; w < kBwdThreads / 32; ++w) a += s_warp[w][v];
-                st_async_f32(map_to_rank(smem_u32(&s_peer[q][rank][v]), (uint32_t)dst), a, map_to_rank(bar, (uint32_t)dst));
-            }
-        }
-        if (i >= 1) { // ------------------------------------------------------------- pass 2, group i-1
-            const int ip = i - 1;
-            const int64_t grp = cid + (int64_t)ip * nclusters;
-            const int stage = ip % kBwdStages, q = ip % kSumSlots;
-            mbar_wait(smem_u32(&s_sum[q]), (uint32_t)(ip / kSumSlots) & 1u);
-            float t = 0.f;
-            if (lane < 2 * S)
-                for (int r = 0; r < (int)cs; ++r) t += s_peer[q][r][lane];
-#pragma unroll
-            for (int k = 0; k < S; ++k) {
-                const float t1 = __shfl_sync(0xffffffffu, t, 2 * k), t2 = __shfl_sync(0xffffffffu, t, 2 * k + 1);
-                const int64_t smp = grp * S + k;
-                if (active && smp < B) {
-                    const float rs = rstd_in[smp], nmr = -mean_in[smp] * rs;
-                    const float a = -(t1 * inv_d * rs), b = -(t2 * inv_d * rs); // -m1 * rstd, -m2 * rstd
-                    const f2 rs2 = f2_make(rs, rs), nmr2 = f2_make(nmr, nmr), a2 = f2_make(a, a), b2 = f2_make(b, b);
-                    const uint4 xv = stage_ptr(stage, k, 0)[tid], dv = stage_ptr(stage, k, 1)[tid];
-                    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
-                    if (HAS_RES) rv = stage_ptr(stage, k, 2)[tid];
-                    uint32_t ow[4];
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        f2 z = f2_add(bf2_to_f2(word_of(xv, p)), bf2_to_f2(word_of(cbv, p)));
-                        if (HAS_RES) z = f2_add(z, bf2_to_f2(word_of(rv, p)));
-                        const f2 hh = f2_fma(z, rs2, nmr2);
-                        const uint32_t dw = word_of(dv, p), mk = mask_prev[k] >> (2 * p);
-                        const f2 gy = f2_make((mk & 1u) ? __uint_as_float(dw << 16) : 0.f,
-                                              (mk & 2u) ? __uint_as_float(dw & 0xFFFF0000u) : 0.f);
-                        const f2 ww = f2_mul(gy, bf2_to_f2(word_of(gv, p)));
-                        const f2 o = f2_fma(hh, b2, f2_fma(ww, rs2, a2)); // w*rstd - m1*rstd - h*m2*rstd
-                        dcb[p] = f2_add(dcb[p], o);
-                        ow[p] = f2_to_bf2(o);
-                    }
-                    dx[smp * nvec + slot] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                }
+                for (int p = 0; p < 4; ++p) h[k][p] = w[k][p] = f2_make(0.f, 0.f);
             }
         }
 #pragma unroll
-        for (int k = 0; k < S; ++k) mask_prev[k] = mask_cur[k];
-        __syncthreads(); // ring stage (i-1) % 3 and s_warp are free again
-        if (tid == 0 && i + 2 < G) issue(i + 2);
+        for (int k = 0; k < S; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                p1[k] += __shfl_xor_sync(0xffffffffu, p1[k], o);
+                p2[k] += __shfl_xor_sync(0xffffffffu, p2[k], o);
+            }
+            if (lane == 0) {
+                s_warp[warp][2 * k] = p1[k];
+                s_warp[warp][2 * k + 1] = p2[k];
+            }
+        }
+        __syncthreads(); // s_warp is complete, and every thread is done reading ring stage `stage`
+        if (tid == 0 && i + kBwdStages < G) issue(i + kBwdStages);
+        // ---------------------------------------------------------------- exchange
+        // This CTA's 2*S sums go to every CTA of the cluster (itself included); the receiver's mbarrier
+        // counts the bytes. Two slots are enough: a peer sends group i+1 only after it has passed its
+        // wait for group i, and it sends group i+2 only after THIS CTA's sums of i+1 -- sent after all
+        // its warps finished reading slot i -- have reached it. For the same reason s_warp is not
+        // overwritten early: no warp passes the wait below before warp 0 has read s_warp and sent.
+        const uint32_t bar = smem_u32(&s_sum[q]);
+        if (tid == 0) mbar_expect_tx(bar, sum_bytes);
+        for (int e = tid; e < 2 * S * (int)cs; e += kBwdThreads) {
+            const int v = e % (2 * S), dst = e / (2 * S);
+            float a = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < kBwdThreads / 32; ++ww) a += s_warp[ww][v];
+            st_async_f32(map_to_rank(smem_u32(&s_peer[q][rank][v]), (uint32_t)dst), a, map_to_rank(bar, (uint32_t)dst));
+        }
+        mbar_wait(bar, (uint32_t)(i / kSumSlots) & 1u);
+        float t = 0.f;
+        if (lane < 2 * S)
+            for (int r = 0; r < (int)cs; ++r) t += s_peer[q][r][lane];
+        // ---------------------------------------------------------------- pass 2 (from registers)
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            const float t1 = __shfl_sync(0xffffffffu, t, 2 * k), t2 = __shfl_sync(0xffffffffu, t, 2 * k + 1);
+            const int64_t smp = grp * S + k;
+            if (active && smp < B) {
+                const float a = -(t1 * inv_d * rs[k]), b = -(t2 * inv_d * rs[k]); // -m1 * rstd, -m2 * rstd
+                const f2 rs2 = f2_make(rs[k], rs[k]), a2 = f2_make(a, a), b2 = f2_make(b, b);
+                uint32_t ow[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const f2 o = f2_fma(h[k][p], b2, f2_fma(w[k][p], rs2, a2)); // w*rstd - m1*rstd - h*m2*rstd
+                    dcb[p] = f2_add(dcb[p], o);
+                    ow[p] = f2_to_bf2(o);
+                }
+                dx[smp * nvec + slot] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+        }
     }
 
     if (active) {
@@ -798,7 +782,7 @@ int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *
         static int use_cluster = -1;
         if (use_cluster < 0) {
             const char *e = getenv("INV_LN_BWD");
-            use_cluster = (e && e[0] == 'p') ? 0 : 1;
+            use_cluster = (e && e[0] == 'p' && e[1] == 'e') ? 0 : 1; // "percta"
         }
         if (!use_cluster)
             return ln_relu_bwd_percta(dy, x, res, cbias, gamma, beta, mean, rstd, B, D, C, dx, dgamma, dbeta, dcbias,
