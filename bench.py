@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--difficulty", choices=["easy", "hard"], default="hard")
     ap.add_argument("--max-episode-steps", type=int, default=500)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=4, help="timed host-buffer steps (0 = skip e2e)")
+    ap.add_argument("--e2e-steps", type=int, default=8, help="timed host-buffer steps (0 = skip e2e)")
     ap.add_argument("--e2e-envs", type=int, default=0, help="envs per GPU for the e2e leg (0 = same as --envs-per-gpu)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg (0 = skip)")
     ap.add_argument("--cpu-sample-envs", type=int, default=65536)

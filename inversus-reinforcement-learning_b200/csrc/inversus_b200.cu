@@ -576,7 +576,9 @@ static int ensure_host_staging(inv_sim *s)
     const size_t n = (size_t)s->n;
     if (!s->h_a1) CUDA_TRY(cudaMallocHost((void **)&s->h_a1, n));
     if (!s->h_a2) CUDA_TRY(cudaMallocHost((void **)&s->h_a2, n));
-    if (!s->h_small && s->small_bytes <= kStagedSmallMax) CUDA_TRY(cudaMallocHost((void **)&s->h_small, s->small_bytes));
+    size_t staged_max = kStagedSmallMax;
+    if (const char *e = getenv("INV_HOST_STAGED_MAX")) staged_max = (size_t)atoll(e); // tests: force the direct-copy path
+    if (!s->h_small && s->small_bytes <= staged_max) CUDA_TRY(cudaMallocHost((void **)&s->h_small, s->small_bytes));
     return INV_OK;
 }
 
@@ -676,7 +678,7 @@ int inv_step_host(inv_sim *s, const int8_t *a1, const int8_t *a2, void *obs_p1, 
     // small outputs only: what is not overlapped is the LAST chunk's copy, so the chunks shrink
     // towards the end (3 : 3 : 1 : 1)
     int64_t bounds[kMaxHostChunks + 1];
-    const bool tapered = !(obs_p1 || obs_p2) && nchunks == 4 && !getenv("INV_HOST_CHUNKS");
+    const bool tapered = !(obs_p1 || obs_p2) && nchunks == 4;
     for (int c = 0; c <= nchunks; ++c) {
         int64_t b = tapered ? (n * (c == 0 ? 0 : c == 1 ? 3 : c == 2 ? 6 : c == 3 ? 7 : 8) / 8) & ~(int64_t)255
                             : (int64_t)c * per;

@@ -55,3 +55,21 @@ def test_b200_arm_line():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 16384 and e["d2h_bytes_per_step"] > 16384 * 256
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+@pytest.mark.gpu
+def test_b200_arm_ppo_block():
+    """The PPO block of the line (BASELINE.json configs[3] / configs[4] + the labelled epochs=1 run), at toy sizes."""
+    d = _run(["--envs-per-gpu", "16384", "--steps", "4", "--warmup", "3", "--e2e-steps", "0", "--cpu-seconds", "0",
+              "--ppo", "1", "--ppo-envs3", "2048", "--ppo-envs4", "4096", "--ppo-samples", "32768", "--ppo-iters", "2"],
+             timeout=900)
+    p = d["ppo"]
+    assert p["metric"] == "ppo_samples_per_sec" and p["bf16_peak_tflops"] > 0
+    runs = p["runs"]
+    assert [r["epochs"] for r in runs] == [4, 4, 1] and [r["mode"] for r in runs] == ["selfplay", "vs_dummy", "vs_dummy"]
+    assert "NOT the reference schedule" in runs[2]["run"]
+    for r in runs:
+        assert r["samples_per_s"] > 0 and r["rollout_env_steps_per_s"] > 0 and r["update_samples_per_s"] > 0
+        assert r["iterations_timed"] >= 1 and r["packed_encoder"] is True and r["precision"] == "bf16"
+        assert 0 < r["update_frac_of_bf16_sustained"] < 1 and 0 < r["inference_frac_of_bf16_sustained"] < 1
+        assert r["allreduce"] is None  # one GPU: no collective

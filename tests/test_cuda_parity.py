@@ -192,6 +192,53 @@ def test_host_buffer_paths_deliver_identical_observations(mode):
     assert 0.0 <= sims["auto"][0].host_path()["dma_fraction"] <= 0.9
 
 
+@pytest.mark.parametrize("chunks", [2, 3, 4, 8])
+def test_chunked_host_pipeline_delivers_the_same_bytes(chunks, monkeypatch):
+    """inv_step_host cuts large batches into env chunks (kernel c+1 overlaps the copies of chunk c,
+    direct copies into the caller's arrays, tapered chunks when no observation is requested). Forced
+    here at a small batch: every output must equal the single-chunk call and the device views."""
+    import torch
+    from inversus_b200 import BatchedInversus
+    n, T = 7000, 10
+    monkeypatch.setenv("INV_HOST_STAGED_MAX", "0")        # small outputs go straight to the caller's arrays
+    rs = np.random.RandomState(5)
+    for mode in ("dummy", "selfplay"):
+        monkeypatch.delenv("INV_HOST_CHUNKS", raising=False)
+        ref = BatchedInversus(n, mode, "hard", 25, seed=3, auto_reset=True)
+        got = BatchedInversus(n, mode, "hard", 25, seed=3, auto_reset=True)
+        ref.reset()
+        got.reset()
+        ro, go = ref.host_buffers(pinned=True), got.host_buffers(pinned=False)
+        small = {k: v for k, v in go.items() if not k.startswith("obs")}
+        for t in range(T):
+            a1 = rs.randint(0, 13, n).astype(np.int8)
+            a2 = rs.randint(0, 13, n).astype(np.int8) if mode == "selfplay" else None
+            monkeypatch.delenv("INV_HOST_CHUNKS", raising=False)
+            ref.set_host_path(0, 0.0)
+            ref.step_host(a1, a2, ro)
+            monkeypatch.setenv("INV_HOST_CHUNKS", str(chunks))
+            got.set_host_path(3 if t % 2 else 0, 0.4)      # plain copies and packed rows + host expansion
+            if t % 3 == 2:
+                for v in small.values():
+                    if isinstance(v, np.ndarray):
+                        v[...] = 0
+                got.step_host(a1, a2, small)                # no observation requested: tapered chunks
+                keys = [k for k in small if k != "_pins"]
+            else:
+                got.step_host(a1, a2, go)
+                keys = [k for k in go if k != "_pins"]
+            for k in keys:
+                assert np.array_equal(go[k], ro[k]), (mode, chunks, t, k)
+            assert torch.equal(got.packed_state, ref.packed_state)
+        assert got.poll_status() == 0
+        with pytest.raises(ValueError):
+            bad = np.zeros(n, np.int8)
+            bad[n - 1] = 13
+            got.step_host(bad, bad if mode == "selfplay" else None, go)
+        ref.close()
+        got.close()
+
+
 @pytest.mark.parametrize("dtype", ["f32", "bf16", "u8"])
 def test_indexed_reset_for_every_observation_dtype(dtype):
     """MultiEnvRunner.envs[i].reset() path (inv_reset_envs) for all obs dtypes and both views:
