@@ -419,21 +419,32 @@ encode_bwd_kernel(const uint32_t *__restrict__ planes, int64_t stride, int64_t c
     }
 }
 
-// One thread per OUTPUT element: dgamma[4800], dbeta[4800], dw1[32*12*9], db1[32].
-__global__ void encode_reduce_kernel(const float *__restrict__ partials, int nparts, float *__restrict__ dw1,
-                                     float *__restrict__ db1, float *__restrict__ dgamma, float *__restrict__ dbeta)
+// Stage 1 of the reduction: red[i] = sum over CTAs of partials[cta][i]. 32 outputs x 8 part groups per
+// block (a thread per output alone would walk the 148 partials one latency at a time).
+__global__ void __launch_bounds__(256) encode_sum_partials_kernel(const float *__restrict__ partials, int nparts,
+                                                                   float *__restrict__ red)
+{
+    __shared__ float s[8][33];
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    float a = 0.f;
+    if (i < kPartial)
+        for (int p = threadIdx.y; p < nparts; p += 8) a += partials[(size_t)p * kPartial + i];
+    s[threadIdx.y][threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.y == 0 && i < kPartial) {
+        float t = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) t += s[y][threadIdx.x];
+        red[i] = t;
+    }
+}
+
+// Stage 2, one thread per OUTPUT element: dgamma[4800], dbeta[4800], dw1[32*12*9], db1[32].
+__global__ void encode_reduce_kernel(const float *__restrict__ red, float *__restrict__ dw1, float *__restrict__ db1,
+                                     float *__restrict__ dgamma, float *__restrict__ dbeta)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    auto total = [&](int off) { // independent loads, eight in flight (the grid is small: latency, not bandwidth)
-        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        int p = 0;
-        for (; p + 8 <= nparts; p += 8) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] += partials[(size_t)(p + u) * kPartial + off];
-        }
-        for (; p < nparts; ++p) a[0] += partials[(size_t)p * kPartial + off];
-        return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-    };
+    auto total = [&](int off) { return red[off]; };
     if (i < kD) { dgamma[i] = total(i); return; }
     if (i < 2 * kD) { dbeta[i - kD] = total(i); return; }
     int k = i - 2 * kD;
@@ -481,7 +492,7 @@ constexpr size_t kBwdSmem = sizeof(Tables) + (size_t)kBwdWarps * kD * 2 + (size_
 
 extern "C" {
 
-int inv_encode_partials_floats(void) { return sm_count_enc() * kPartial; }
+int inv_encode_partials_floats(void) { return (sm_count_enc() + 1) * kPartial; } // per-CTA partials + their sum
 
 int inv_encode_fwd(const void *packed_dev, int64_t stride, int64_t count, int view, const float *w1, const float *b1,
                    const float *gamma_hwc, const float *beta_hwc, float eps, void *y_out, float *extra_out,
@@ -530,8 +541,10 @@ int inv_encode_bwd(const void *packed_dev, int64_t stride, int64_t count, int vi
         static_cast<const uint32_t *>(packed_dev), stride, count, view, w1, b1, reinterpret_cast<const float2 *>(gamma_hwc),
         reinterpret_cast<const float2 *>(beta_hwc), mean, rstd, static_cast<const uint32_t *>(dy), partials);
     if (cudaGetLastError() != cudaSuccess) return INV_ERR_CUDA;
+    float *red = partials + (size_t)sm_count_enc() * kPartial;
+    encode_sum_partials_kernel<<<(kPartial + 31) / 32, dim3(32, 8), 0, st>>>(partials, grid, red);
     const int outputs = 2 * kD + kCo * kCi * 9 + kCo;
-    encode_reduce_kernel<<<(outputs + 127) / 128, 128, 0, st>>>(partials, grid, dw1, db1, dgamma_hwc, dbeta_hwc);
+    encode_reduce_kernel<<<(outputs + 127) / 128, 128, 0, st>>>(red, dw1, db1, dgamma_hwc, dbeta_hwc);
     return cudaGetLastError() == cudaSuccess ? INV_OK : INV_ERR_CUDA;
 }
 

@@ -95,7 +95,7 @@ for Bp in (8192, 65536):
                 for _ in range(3):
                     train_step_packed()
                 torch.cuda.synchronize()
-            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=24, max_name_column_width=70))
+            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
     sim.close()
 
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
