@@ -270,9 +270,10 @@ int inv_encode_bwd(const void *packed_dev, int64_t stride, int64_t count, int vi
  * (csrc/wgrad_kernels.cu), for the policy's conv3 / conv4 (inversus_rl/policies.py:36-43):
  *   dw[co][ky][kx][ci] = sum over (n, y, x) of dy[n, y, x, co] * x[n, y + ky - 1, x + kx - 1, ci]
  * dy: [B,10,15,cout] bf16 and x: [B,10,15,cin] bf16, both channels-last and 16-byte aligned;
- * cout = 128, cin = 64 or 128. dw: [cout][3][3][cin] fp32 (the memory order of a channels-last
- * filter). partials: scratch of inv_conv3x3_wgrad_scratch_floats(cin) floats. Deterministic. */
-int64_t inv_conv3x3_wgrad_scratch_floats(int32_t cin);
+ * (cout, cin) = (128, 128), (128, 64) or (64, 32): conv4, conv3, conv2. dw: [cout][3][3][cin] fp32 (the
+ * memory order of a channels-last filter). partials: scratch of
+ * inv_conv3x3_wgrad_scratch_floats(cin, cout) floats. Deterministic. */
+int64_t inv_conv3x3_wgrad_scratch_floats(int32_t cin, int32_t cout);
 int inv_conv3x3_wgrad(const void *dy, const void *x, int64_t B, int32_t cin, int32_t cout, float *dw, float *partials,
                       void *stream);
 

@@ -80,7 +80,7 @@ SYMBOLS = {
     "inv_encode_partials_floats": (C.c_int, []),
     "inv_encode_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int] + [C.c_void_p] * 4 + [C.c_float] + [C.c_void_p] * 5),
     "inv_encode_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int] + [C.c_void_p] * 13),
-    "inv_conv3x3_wgrad_scratch_floats": (C.c_int64, [C.c_int32]),
+    "inv_conv3x3_wgrad_scratch_floats": (C.c_int64, [C.c_int32, C.c_int32]),
     "inv_conv3x3_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "inv_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32,
                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

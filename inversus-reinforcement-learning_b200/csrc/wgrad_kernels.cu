@@ -20,6 +20,9 @@
 //     the reduction dimension): 128-byte-swizzled rows of 64 channels, 8 rows per 1 KB atom.
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue, which
 //     runs once: TMEM -> registers -> per-CTA fp32 partials; a small kernel sums the partials.
+//   * conv2 (32 -> 64 channels) uses the same kernel with M = 64, N = 32: all nine taps fit one CTA's
+//     TMEM (9 x 32 columns), so dY is loaded once per sample and X as three kx-shifted boxes of
+//     64-byte rows (64-byte swizzle).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -29,17 +32,28 @@
 
 namespace {
 
-constexpr int kCout = 128;
 constexpr int kBoxW = 16;                 // 15 board columns + 1 (zero-filled or neighbour halo)
 constexpr int kRowsA = 10 * kBoxW;        // 160 positions of dY per sample (K of the GEMM)
 constexpr int kRowsB = 12 * kBoxW;        // 192 positions of X per sample: rows y = -1 .. 10
-constexpr int kHalfA = kRowsA * 128;      // bytes of one 64-channel half of the dY tile
-constexpr int kHalfB = kRowsB * 128;      // bytes of one 64-channel half of the X tile
 constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 512;
 
-template <int CIN> __host__ __device__ constexpr int stage_bytes() { return 2 * kHalfA + (CIN / 64) * kHalfB; }
-template <int CIN> __host__ __device__ constexpr int num_stages() { return CIN == 128 ? 2 : 3; }
+// Shape of one instantiation. NKX = kernel columns handled by one CTA (3 ky each).
+template <int COUT, int CIN, int NKX>
+struct Shape {
+    static_assert((COUT == 128 || COUT == 64) && (CIN == 128 || CIN == 64 || CIN == 32) && (NKX == 1 || NKX == 3), "unsupported shape");
+    static constexpr int kAHalves = COUT / 64;               // 64-channel column blocks of the dY tile
+    static constexpr int kHalfA = kRowsA * 128;              // bytes of one block (128-byte rows)
+    static constexpr int kBRowBytes = CIN >= 64 ? 128 : 64;  // X rows: 64 or 32 channels per swizzled row
+    static constexpr int kBHalves = CIN >= 64 ? CIN / 64 : 1;
+    static constexpr int kHalfB = kRowsB * kBRowBytes;
+    static constexpr int kBBox = kBHalves * kHalfB;          // one kx-shifted X tile
+    static constexpr int kStageBytes = kAHalves * kHalfA + NKX * kBBox;
+    static constexpr int kStages = kStageBytes > 80 * 1024 ? 2 : 3;
+    static constexpr uint32_t kBLayout = CIN >= 64 ? 2u : 4u; // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
+    static constexpr uint32_t kBSbo = CIN >= 64 ? 1024u : 512u; // bytes between 8-row groups
+    static_assert(NKX * 3 * CIN <= (int)kTmemCols, "accumulators exceed TMEM");
+};
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -74,10 +88,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map
 // shared-memory matrix descriptor, MN-major, 128-byte swizzle (cute::UMMA::SmemDescriptor):
 // start address, leading-dimension byte offset (between 64-element column blocks), stride byte
 // offset (between 8-row groups along K), version 1, layout type 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2u)
 {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = bf16, both MN-major
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N)
@@ -98,18 +112,20 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 }
 
 // partials: [parts][ky][kx][co][CIN] fp32
-template <int CIN>
+template <int COUT, int CIN, int NKX>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, int64_t B,
                      int per_part, float *__restrict__ partials)
 {
-    constexpr int STAGES = num_stages<CIN>();
-    constexpr int SB = stage_bytes<CIN>();
+    typedef Shape<COUT, CIN, NKX> S;
+    constexpr int STAGES = S::kStages;
+    constexpr int SB = S::kStageBytes;
+    constexpr int KXG = 3 / NKX; // CTAs that share a sample range, one per group of kernel columns
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES], s_done;
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kx = blockIdx.x % 3, part = blockIdx.x / 3;
+    const int kx0 = (blockIdx.x % KXG) * NKX, part = blockIdx.x / KXG;
     const int64_t first = (int64_t)part * per_part;
     const int64_t last = first + per_part < B ? first + per_part : B;
     const int nsamp = last > first ? (int)(last - first) : 0;
@@ -123,7 +139,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
         mbar_init(smem_addr(&s_done), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) { // TMEM: the three accumulators (3 x CIN columns) in one 512-column allocation
+    if (warp == 1) { // TMEM: the NKX x 3 accumulators (CIN columns each) in one 512-column allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -139,32 +155,41 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
                 const int st = i % STAGES;
                 if (i >= STAGES) mbar_wait(smem_addr(&s_empty[st]), (uint32_t)((i / STAGES) - 1) & 1u);
                 const uint32_t bar = smem_addr(&s_full[st]);
-                const uint32_t a0 = base + (uint32_t)st * SB, b0 = a0 + 2 * kHalfA;
+                const uint32_t a0 = base + (uint32_t)st * SB, b0 = a0 + S::kAHalves * S::kHalfA;
                 mbar_expect_tx(bar, (uint32_t)SB);
                 const int n = (int)(first + i);
-                tma_load_4d(a0, &map_dy, 0, 0, 0, n, bar);
-                tma_load_4d(a0 + kHalfA, &map_dy, 64, 0, 0, n, bar);
 #pragma unroll
-                for (int h = 0; h < CIN / 64; ++h) tma_load_4d(b0 + h * kHalfB, &map_x, 64 * h, kx - 1, -1, n, bar);
+                for (int h = 0; h < S::kAHalves; ++h) tma_load_4d(a0 + h * S::kHalfA, &map_dy, 64 * h, 0, 0, n, bar);
+#pragma unroll
+                for (int k = 0; k < NKX; ++k)
+#pragma unroll
+                    for (int h = 0; h < S::kBHalves; ++h)
+                        tma_load_4d(b0 + k * S::kBBox + h * S::kHalfB, &map_x, 64 * h, kx0 + k - 1, -1, n, bar);
             }
         }
     } else if (warp == 1) {
         // ================================================================= MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(kCout, CIN);
+            // With several kernel columns per CTA (conv2) their X boxes sit side by side in the MMA's N
+            // dimension: one MMA of N = NKX * CIN per kernel row, the column blocks LBO = one box apart.
+            // Accumulator of kernel row ky: columns [ky * NKX * CIN, +NKX * CIN), kx-major inside.
+            constexpr uint32_t idesc = umma_idesc(COUT, NKX * CIN);
+            constexpr uint32_t lbo_b = NKX > 1 ? (uint32_t)S::kBBox : (uint32_t)S::kHalfB;
+            static_assert(NKX == 1 || S::kBHalves == 1, "merged kernel columns need one column block per box");
             for (int i = 0; i < nsamp; ++i) {
                 const int st = i % STAGES;
                 mbar_wait(smem_addr(&s_full[st]), (uint32_t)(i / STAGES) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a0 = base + (uint32_t)st * SB, b0 = a0 + 2 * kHalfA;
+                const uint32_t a0 = base + (uint32_t)st * SB, b0 = a0 + S::kAHalves * S::kHalfA;
+                // 30 MMAs per sample, 16 positions (one board row) each. Order measured per shape
+                // (profiles/r2_wgrad.txt): row-by-row per accumulator for the large shapes, accumulators
+                // interleaved for conv2's small MMAs.
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-                    for (int kk = 0; kk < kRowsA / 16; ++kk) { // 16 positions (one board row) per MMA
-                        const uint64_t da = umma_desc(a0 + kk * 16 * 128, kHalfA, 1024);
-                        const uint64_t db = umma_desc(b0 + (ky * 16 + kk * 16) * 128, kHalfB, 1024);
-                        umma_f16(tmem + ky * CIN, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                    }
+                for (int t = 0; t < 3 * (kRowsA / 16); ++t) {
+                    const int ky = NKX > 1 ? t % 3 : t / (kRowsA / 16), kk = NKX > 1 ? t / 3 : t % (kRowsA / 16);
+                    const uint64_t da = umma_desc(a0 + kk * 16 * 128, S::kHalfA, 1024);
+                    const uint64_t db = umma_desc(b0 + (ky * 16 + kk * 16) * S::kBRowBytes, lbo_b, S::kBSbo, S::kBLayout);
+                    umma_f16(tmem + ky * NKX * CIN, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
                 }
                 umma_commit(smem_addr(&s_empty[st])); // the stage is free once these MMAs have read it
             }
@@ -172,20 +197,24 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
         }
     } else {
         // ================================================================= epilogue (once)
-        const int q = warp & 3; // TMEM lane quadrant this warp may read
-        const int co = q * 32 + lane;
+        // TMEM lane quadrant q belongs to warp q (mod 4). M = 128: accumulator row = lane index;
+        // M = 64: rows 16q .. 16q+15 sit in the first 16 lanes of quadrant q.
+        const int q = warp & 3;
+        const int co = COUT == 128 ? q * 32 + lane : q * 16 + lane;
+        const bool row_ok = COUT == 128 || lane < 16;
         if (nsamp > 0) {
             mbar_wait(smem_addr(&s_done), 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
 #pragma unroll 1
-        for (int ky = 0; ky < 3; ++ky) {
-            float *out = partials + ((((size_t)part * 3 + ky) * 3 + kx) * kCout + co) * CIN;
+        for (int t = 0; t < NKX * 3; ++t) {
+            const int k = t / 3, ky = t % 3;
+            float *out = partials + ((((size_t)part * 3 + ky) * 3 + (kx0 + k)) * COUT + co) * CIN;
 #pragma unroll 1
             for (int c = 0; c < CIN / 32; ++c) {
                 uint32_t v[32];
                 if (nsamp > 0) {
-                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ky * CIN + c * 32);
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((ky * NKX + k) * CIN + c * 32);
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                                  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -199,9 +228,11 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = 0u;
                 }
-                uint4 *o4 = reinterpret_cast<uint4 *>(out + c * 32);
+                if (row_ok) {
+                    uint4 *o4 = reinterpret_cast<uint4 *>(out + c * 32);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 8; ++j) o4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
             }
         }
     }
@@ -211,12 +242,12 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
 }
 
 // dw[co][ky][kx][ci] = sum over parts of partials[part][ky][kx][co][ci]
-__global__ void wgrad_reduce_kernel(const float *__restrict__ partials, int parts, int cin, float *__restrict__ dw)
+__global__ void wgrad_reduce_kernel(const float *__restrict__ partials, int parts, int cin, int cout, float *__restrict__ dw)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = 9 * kCout * cin;
+    const int total = 9 * cout * cin;
     if (i >= total) return;
-    const int ci = i % cin, co = (i / cin) % kCout, tap = i / (cin * kCout);
+    const int ci = i % cin, co = (i / cin) % cout, tap = i / (cin * cout);
     float a = 0.f;
 #pragma unroll 8
     for (int p = 0; p < parts; ++p) a += partials[(size_t)p * total + i];
@@ -245,12 +276,14 @@ bool make_map(CUtensorMap *map, const void *ptr, int64_t B, int C, int box_rows)
 {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return false;
+    const int inner = C >= 64 ? 64 : C; // channels per swizzled row: 128-byte rows, or 64-byte rows for C = 32
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)INV_BOARD_W, (cuuint64_t)INV_BOARD_H, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * INV_BOARD_W, (cuuint64_t)C * 2 * INV_BOARD_W * INV_BOARD_H};
-    const cuuint32_t box[4] = {64, (cuuint32_t)kBoxW, (cuuint32_t)box_rows, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)inner, (cuuint32_t)kBoxW, (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -267,28 +300,30 @@ int sm_count_wg()
     return n[dev];
 }
 
-template <int CIN>
+template <int COUT, int CIN, int NKX>
 int launch_wgrad(const void *dy, const void *x, int64_t B, float *dw, float *partials, cudaStream_t st)
 {
+    typedef Shape<COUT, CIN, NKX> S;
     CUtensorMap map_dy, map_x;
-    if (!make_map(&map_dy, dy, B, kCout, 10) || !make_map(&map_x, x, B, CIN, 12)) return INV_ERR_CUDA;
-    constexpr size_t smem = (size_t)num_stages<CIN>() * stage_bytes<CIN>() + 1024;
+    if (!make_map(&map_dy, dy, B, COUT, 10) || !make_map(&map_x, x, B, CIN, 12)) return INV_ERR_CUDA;
+    constexpr size_t smem = (size_t)S::kStages * S::kStageBytes + 1024;
+    auto kern = conv3x3_wgrad_kernel<COUT, CIN, NKX>;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        if (cudaFuncSetAttribute(conv3x3_wgrad_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return INV_ERR_CUDA;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return INV_ERR_CUDA;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    int parts = sm_count_wg() / 3;
+    constexpr int KXG = 3 / NKX;
+    int parts = sm_count_wg() / KXG;
     if (parts > B) parts = (int)B;
     if (parts < 1) parts = 1;
     const int per_part = (int)((B + parts - 1) / parts);
-    conv3x3_wgrad_kernel<CIN><<<3 * parts, kThreads, smem, st>>>(map_dy, map_x, B, per_part, partials);
+    kern<<<KXG * parts, kThreads, smem, st>>>(map_dy, map_x, B, per_part, partials);
     if (cudaGetLastError() != cudaSuccess) return INV_ERR_CUDA;
-    const int total = 9 * kCout * CIN;
-    wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partials, parts, CIN, dw);
+    const int total = 9 * COUT * CIN;
+    wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(partials, parts, CIN, COUT, dw);
     return cudaGetLastError() == cudaSuccess ? INV_OK : INV_ERR_CUDA;
 }
 
@@ -296,15 +331,22 @@ int launch_wgrad(const void *dy, const void *x, int64_t B, float *dw, float *par
 
 extern "C" {
 
-int64_t inv_conv3x3_wgrad_scratch_floats(int32_t cin) { return (int64_t)(sm_count_wg() / 3) * 9 * kCout * cin; }
+int64_t inv_conv3x3_wgrad_scratch_floats(int32_t cin, int32_t cout)
+{
+    const int kxg = (cout == 64 && cin == 32) ? 1 : 3; // CTAs per sample range
+    return (int64_t)(sm_count_wg() / kxg) * 9 * cout * cin;
+}
 
 int inv_conv3x3_wgrad(const void *dy, const void *x, int64_t B, int32_t cin, int32_t cout, float *dw, float *partials,
                       void *stream)
 {
-    if (!dy || !x || !dw || !partials || B <= 0 || cout != kCout || (cin != 64 && cin != 128)) return INV_ERR_INVALID_ARG;
+    if (!dy || !x || !dw || !partials || B <= 0) return INV_ERR_INVALID_ARG;
     if (((uintptr_t)dy | (uintptr_t)x) & 15u) return INV_ERR_INVALID_ARG;
-    return cin == 128 ? launch_wgrad<128>(dy, x, B, dw, partials, (cudaStream_t)stream)
-                      : launch_wgrad<64>(dy, x, B, dw, partials, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cout == 128 && cin == 128) return launch_wgrad<128, 128, 1>(dy, x, B, dw, partials, st);
+    if (cout == 128 && cin == 64) return launch_wgrad<128, 64, 1>(dy, x, B, dw, partials, st);
+    if (cout == 64 && cin == 32) return launch_wgrad<64, 32, 3>(dy, x, B, dw, partials, st);
+    return INV_ERR_INVALID_ARG;
 }
 
 } // extern "C"

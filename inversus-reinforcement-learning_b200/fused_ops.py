@@ -226,7 +226,7 @@ class _Conv3x3(torch.autograd.Function):
             lib = _capi.load()
             out = torch.empty((cout, 3, 3, cin), dtype=torch.float32, device=x.device)
             with torch.cuda.device(x.device):
-                scratch = torch.empty(lib.inv_conv3x3_wgrad_scratch_floats(cin), dtype=torch.float32, device=x.device)
+                scratch = torch.empty(lib.inv_conv3x3_wgrad_scratch_floats(cin, cout), dtype=torch.float32, device=x.device)
                 _capi.check(lib.inv_conv3x3_wgrad(dy.data_ptr(), x.data_ptr(), B, cin, cout, out.data_ptr(),
                                                   scratch.data_ptr(), _stream(x)))
             dw = out.permute(0, 3, 1, 2).to(w.dtype)  # logical [co, ci, ky, kx], channels-last strides like w
@@ -235,7 +235,7 @@ class _Conv3x3(torch.autograd.Function):
 
 def conv3x3_supported(x: torch.Tensor, w: torch.Tensor) -> bool:
     return (x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.dim() == 4
-            and tuple(x.shape[2:]) == (10, 15) and w.shape[0] == 128 and w.shape[1] in (64, 128)
+            and tuple(x.shape[2:]) == (10, 15) and (w.shape[0], w.shape[1]) in ((128, 128), (128, 64), (64, 32))
             and tuple(w.shape[2:]) == (3, 3) and x.is_contiguous(memory_format=torch.channels_last))
 
 

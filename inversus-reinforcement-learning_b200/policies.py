@@ -41,7 +41,7 @@ class InversusCNNPolicy(nn.Module):
         self.flatten = nn.Flatten()
         self.feature_dim = _CONV_WIDTHS[-1] * height * width
         self.use_fused_kernels = True  # CUDA only: fused LayerNorm(+residual)+ReLU kernels in forward_bf16
-        self.use_custom_wgrad = True   # CUDA only: tcgen05 weight gradient for conv3 / conv4 when training
+        self.use_custom_wgrad = True   # CUDA only: tcgen05 weight gradient for conv2 / conv3 / conv4 when training
         self._weights_epoch = 0        # bumped by mark_updated(); part of the inference-cache key
         self.fc_actor = _mlp_head(self.feature_dim + extra_dim, hidden_dim, NUM_ACTIONS)
         self.fc_critic = _mlp_head(self.feature_dim + extra_dim, hidden_dim, 1)
@@ -132,7 +132,7 @@ class InversusCNNPolicy(nn.Module):
         for i in ((2, 3, 4) if packed else (1, 2, 3, 4)):
             # fused path: cuDNN runs bias-free, the per-channel bias is added inside the LayerNorm kernel
             w_i = prep[f"cw{i}"]
-            if fused and self.use_custom_wgrad and w_i.requires_grad and i >= 3:
+            if fused and self.use_custom_wgrad and w_i.requires_grad and i >= 2:
                 # training: library forward / input gradient, tcgen05 weight gradient (csrc/wgrad_kernels.cu)
                 from .fused_ops import conv3x3, conv3x3_supported
                 y = conv3x3(x, w_i) if conv3x3_supported(x, w_i) else F.conv2d(x, w_i, None, padding=1)

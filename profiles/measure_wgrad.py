@@ -25,19 +25,19 @@ def bench(fn, n=20, warm=5):
 
 lib = _capi.load()
 st = int(torch.cuda.current_stream().cuda_stream)
-for cin in (128, 64):
+for cin, cout in ((128, 128), (64, 128), (32, 64)):
     for B in (8192, 32768):
         x = torch.randn(B, cin, 10, 15, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        dy = torch.randn(B, 128, 10, 15, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        w = torch.randn(128, cin, 3, 3, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        out = torch.empty((128, 3, 3, cin), dtype=torch.float32, device="cuda")
-        scratch = torch.empty(lib.inv_conv3x3_wgrad_scratch_floats(cin), dtype=torch.float32, device="cuda")
+        dy = torch.randn(B, cout, 10, 15, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        w = torch.randn(cout, cin, 3, 3, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        out = torch.empty((cout, 3, 3, cin), dtype=torch.float32, device="cuda")
+        scratch = torch.empty(lib.inv_conv3x3_wgrad_scratch_floats(cin, cout), dtype=torch.float32, device="cuda")
         ms_lib = bench(lambda: torch.ops.aten.convolution_backward(dy, x, w, None, (1, 1), (1, 1), (1, 1), False, (0, 0), 1,
                                                                    (False, True, False)))
-        ms_own = bench(lambda: lib.inv_conv3x3_wgrad(dy.data_ptr(), x.data_ptr(), B, cin, 128, out.data_ptr(),
+        ms_own = bench(lambda: lib.inv_conv3x3_wgrad(dy.data_ptr(), x.data_ptr(), B, cin, cout, out.data_ptr(),
                                                      scratch.data_ptr(), st))
-        flop = B * 150 * 128 * cin * 9 * 2
-        print(f"wgrad cin={cin} B={B}: library {ms_lib * 1e3:.1f} us ({flop / ms_lib / 1e9:.0f} TFLOP/s)   "
+        flop = B * 150 * cout * cin * 9 * 2
+        print(f"wgrad cin={cin} cout={cout} B={B}: library {ms_lib * 1e3:.1f} us ({flop / ms_lib / 1e9:.0f} TFLOP/s)   "
               f"tcgen05 kernel {ms_own * 1e3:.1f} us ({flop / ms_own / 1e9:.0f} TFLOP/s, "
               f"{(x.numel() + dy.numel()) * 2 / ms_own / 1e6:.0f} GB/s of unique operand bytes)", flush=True)
 

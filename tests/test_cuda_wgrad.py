@@ -5,15 +5,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("cin", [128, 64])
+@pytest.mark.parametrize("cin,cout", [(128, 128), (64, 128), (32, 64)])
 @pytest.mark.parametrize("B", [1, 7, 300])
-def test_conv3x3_weight_gradient_matches_the_library(cin, B):
+def test_conv3x3_weight_gradient_matches_the_library(cin, cout, B):
     import torch
     from inversus_b200.fused_ops import conv3x3, conv3x3_supported
     torch.manual_seed(B * 1000 + cin)
     x = torch.randn(B, cin, 10, 15, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    w = (torch.randn(128, cin, 3, 3, device="cuda") * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    dy = torch.randn(B, 128, 10, 15, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(cout, cin, 3, 3, device="cuda") * 0.05).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(B, cout, 10, 15, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     assert conv3x3_supported(x, w)
     xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
     torch.nn.functional.conv2d(xr, wr, None, padding=1).backward(dy)
