@@ -27,6 +27,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/inversus_b200.h"
 
@@ -41,7 +42,7 @@ constexpr uint32_t kTmemCols = 512;
 // Shape of one instantiation. NKX = kernel columns handled by one CTA (3 ky each).
 template <int COUT, int CIN, int NKX>
 struct Shape {
-    static_assert((COUT == 128 || COUT == 64) && (CIN == 128 || CIN == 64 || CIN == 32) && (NKX == 1 || NKX == 3), "unsupported shape");
+    static_assert((COUT == 128 || COUT == 64) && (CIN == 128 || CIN == 64 || CIN == 32) && NKX >= 1 && NKX <= 3, "unsupported shape");
     static constexpr int kAHalves = COUT / 64;               // 64-channel column blocks of the dY tile
     static constexpr int kHalfA = kRowsA * 128;              // bytes of one block (128-byte rows)
     static constexpr int kBRowBytes = CIN >= 64 ? 128 : 64;  // X rows: 64 or 32 channels per swizzled row
@@ -112,20 +113,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 }
 
 // partials: [parts][ky][kx][co][CIN] fp32
-template <int COUT, int CIN, int NKX>
-__global__ void __launch_bounds__(kThreads, 1)
-conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, int64_t B,
-                     int per_part, float *__restrict__ partials)
+// One CTA: kernel columns [kx0, kx0 + NKX), samples [part * per_part, ...). STAGES ring stages of
+// Shape<COUT, CIN, NKX>::kStageBytes each must fit the dynamic shared memory of the launch.
+template <int COUT, int CIN, int NKX, int STAGES>
+__device__ __forceinline__ void wgrad_cta(const CUtensorMap &map_dy, const CUtensorMap &map_x, int64_t B, int kx0, int part,
+                                          int per_part, float *__restrict__ partials)
 {
     typedef Shape<COUT, CIN, NKX> S;
-    constexpr int STAGES = S::kStages;
     constexpr int SB = S::kStageBytes;
-    constexpr int KXG = 3 / NKX; // CTAs that share a sample range, one per group of kernel columns
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_full[STAGES], s_empty[STAGES], s_done;
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kx0 = (blockIdx.x % KXG) * NKX, part = blockIdx.x / KXG;
     const int64_t first = (int64_t)part * per_part;
     const int64_t last = first + per_part < B ? first + per_part : B;
     const int nsamp = last > first ? (int)(last - first) : 0;
@@ -182,11 +181,12 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a0 = base + (uint32_t)st * SB, b0 = a0 + S::kAHalves * S::kHalfA;
                 // 30 MMAs per sample, 16 positions (one board row) each. Order measured per shape
-                // (profiles/r2_wgrad.txt): row-by-row per accumulator for the large shapes, accumulators
-                // interleaved for conv2's small MMAs.
+                // (profiles/r2_wgrad.txt): row-by-row per accumulator for the large shapes (interleaving
+                // cost conv3 20 %), accumulators interleaved for conv2's small MMAs.
 #pragma unroll
                 for (int t = 0; t < 3 * (kRowsA / 16); ++t) {
-                    const int ky = NKX > 1 ? t % 3 : t / (kRowsA / 16), kk = NKX > 1 ? t / 3 : t % (kRowsA / 16);
+                    constexpr bool kInterleave = CIN < 64;
+                    const int ky = kInterleave ? t % 3 : t / (kRowsA / 16), kk = kInterleave ? t / 3 : t % (kRowsA / 16);
                     const uint64_t da = umma_desc(a0 + kk * 16 * 128, S::kHalfA, 1024);
                     const uint64_t db = umma_desc(b0 + (ky * 16 + kk * 16) * S::kBRowBytes, lbo_b, S::kBSbo, S::kBLayout);
                     umma_f16(tmem + ky * NKX * CIN, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
@@ -241,7 +241,17 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
 }
 
-// dw[co][ky][kx][ci] = sum over parts of partials[part][ky][kx][co][ci]
+// Uniform grid: 3 / NKX CTAs per sample range, one per group of kernel columns.
+template <int COUT, int CIN, int NKX>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, int64_t B,
+                     int per_part, float *__restrict__ partials)
+{
+    constexpr int KXG = 3 / NKX;
+    wgrad_cta<COUT, CIN, NKX, Shape<COUT, CIN, NKX>::kStages>(map_dy, map_x, B, (blockIdx.x % KXG) * NKX, blockIdx.x / KXG,
+                                                             per_part, partials);
+}
+
 __global__ void wgrad_reduce_kernel(const float *__restrict__ partials, int parts, int cin, int cout, float *__restrict__ dw)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -333,7 +343,7 @@ extern "C" {
 
 int64_t inv_conv3x3_wgrad_scratch_floats(int32_t cin, int32_t cout)
 {
-    const int kxg = (cout == 64 && cin == 32) ? 1 : 3; // CTAs per sample range
+    const int kxg = cin == 128 ? 3 : 1; // conv4: three CTAs per sample range; conv2 / conv3: up to one part per SM
     return (int64_t)(sm_count_wg() / kxg) * 9 * cout * cin;
 }
 
