@@ -669,11 +669,10 @@ constexpr size_t smem_bytes()
 }
 
 // ------------------------------------------------------------------------------------------------
-#ifndef INV_MIN_BLOCKS
-#define INV_MIN_BLOCKS 1 // experiments: ask ptxas for more resident CTAs (fewer registers) per SM
-#endif
+// (A minimum-blocks hint was tried: (T, 5) and (T, 6) are slower, and even (T, 1) lets ptxas spend
+// registers and costs 13 %: profiles/r2_variants_f32_b.txt. Plain __launch_bounds__(T) stays.)
 template <int OP, int DT, bool P2V, bool INDEXED, int E, int T = kThreads>
-__global__ void __launch_bounds__(T, INV_MIN_BLOCKS) inv_kernel(const Params p)
+__global__ void __launch_bounds__(T) inv_kernel(const Params p)
 {
     static_assert(E <= T && E % 32 == 0 && T % 32 == 0, "tile must be whole warps");
     extern __shared__ __align__(16) uint32_t smem[];
