@@ -22,6 +22,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "../../include/inversus_b200.h"
 
 namespace {
@@ -369,13 +371,17 @@ __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint
                  "f"(v), "r"(remote_bar)
                  : "memory");
 }
-// spin until the barrier's phase with the given parity has completed; traps instead of hanging
+// Spin until the barrier's phase with the given parity has completed; traps instead of hanging.
+// Default (CTA-scope) acquire on purpose: what is waited for -- TMA bulk copies and the peers'
+// st.async words -- lands in THIS CTA's shared memory through the async proxy and is published by the
+// barrier's own transaction count. A cluster-scope acquire makes ptxas emit CCTL.IVALL (an L1
+// invalidate) after every wait: 26 % of the stall samples of this kernel in the first ncu capture.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t done = 0;
     for (uint32_t spins = 0; !done; ++spins) {
         asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done)
                      : "r"(bar), "r"(parity)
@@ -448,6 +454,7 @@ ln_relu_bwd_cluster_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict
     __shared__ float s_peer[kSumSlots][kMaxCluster][2 * S];
     __shared__ float s_warp[kBwdThreads / 32][2 * S];
     __shared__ float s_cb[kBwdThreads * 8];
+    __shared__ float s_stat[kBwdStages][2 * S]; // rstd[S], mean[S] of the group in each ring stage
 
     // gamma, beta and the conv bias of this thread's 8 columns stay packed (4 registers each);
     // kBwdThreads % cvecs == 0, so slot % cvecs == tid % cvecs
@@ -481,7 +488,15 @@ ln_relu_bwd_cluster_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict
         for (int q = 0; q < kSumSlots; ++q) mbar_init(smem_u32(&s_sum[q]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    cluster_sync_all(); // every CTA's barriers exist before any peer signals them
+    // The groups' mean / rstd travel through shared memory one ring turn ahead, like the tensors: a
+    // global load inside pass 1 sat on the critical path of every group (top stall in the ncu capture).
+    auto stat_load = [&](int i, int j) -> float { // j < S: rstd of sample j, j >= S: mean of sample j - S
+        const int64_t smp = (cid + (int64_t)i * nclusters) * S + (j % S);
+        return smp < B ? (j < S ? rstd_in : mean_in)[smp] : 0.f;
+    };
+    if (tid < 2 * S)
+        for (int q = 0; q < kBwdStages && q < G; ++q) s_stat[q][tid] = stat_load(q, tid);
+    cluster_sync_all(); // every CTA's barriers exist before any peer signals them (and s_stat is visible)
     if (tid == 0) {
         if (G > 0) issue(0);
         if (G > 1) issue(1);
@@ -493,15 +508,20 @@ ln_relu_bwd_cluster_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict
         const int stage = i % kBwdStages, q = i % kSumSlots;
         mbar_wait(smem_u32(&s_full[stage]), (uint32_t)(i / kBwdStages) & 1u);
         // ---------------------------------------------------------------- pass 1
-        f2 h[S][4], w[S][4];
+        // S = 2: h and w stay fp32 pairs (32 registers). S = 4 (no residual): they are parked as bf16
+        // pairs (32 registers again) -- dx is a bf16 output, and twice the samples per exchange
+        // halves the number of cluster exchanges, which is what bounds this kernel.
+        constexpr bool kPack = S > 2;
+        typedef typename std::conditional<kPack, uint32_t, f2>::type hw_t;
+        hw_t h[S][4], w[S][4];
         float p1[S], p2[S], rs[S];
 #pragma unroll
         for (int k = 0; k < S; ++k) {
             p1[k] = p2[k] = rs[k] = 0.f;
             const int64_t smp = grp * S + k;
             if (active && smp < B) {
-                rs[k] = rstd_in[smp];
-                const float nmr = -mean_in[smp] * rs[k];
+                rs[k] = s_stat[stage][k];
+                const float nmr = -s_stat[stage][S + k] * rs[k];
                 const f2 rs2 = f2_make(rs[k], rs[k]), nmr2 = f2_make(nmr, nmr);
                 const uint4 xv = stage_ptr(stage, k, 0)[tid], dv = stage_ptr(stage, k, 1)[tid];
                 uint4 rv = make_uint4(0u, 0u, 0u, 0u);
@@ -521,8 +541,13 @@ ln_relu_bwd_cluster_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict
                     dg[p] = f2_fma(gy, hh, dg[p]);
                     db[p] = f2_add(db[p], gy);
                     const f2 ww = f2_mul(gy, g2);
-                    h[k][p] = hh;
-                    w[k][p] = ww;
+                    if constexpr (kPack) {
+                        h[k][p] = f2_to_bf2(hh);
+                        w[k][p] = f2_to_bf2(ww);
+                    } else {
+                        h[k][p] = hh;
+                        w[k][p] = ww;
+                    }
                     s1 = f2_add(s1, ww);
                     s2 = f2_fma(ww, hh, s2);
                 }
@@ -533,23 +558,39 @@ ln_relu_bwd_cluster_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict
                 p2[k] = b0 + b1;
             } else {
 #pragma unroll
-                for (int p = 0; p < 4; ++p) h[k][p] = w[k][p] = f2_make(0.f, 0.f);
+                for (int p = 0; p < 4; ++p) h[k][p] = w[k][p] = hw_t(0);
             }
         }
+        // Warp reduction of the 2*S sums, transposed: every butterfly step halves the number of values a
+        // lane carries (the half it gives away goes to the partner lane), so 2*S values cost
+        // 2*S - 1 + (5 - log2(2*S)) shuffles instead of 5 * 2*S. Lane l ends with the total of value l / kRep.
+        {
+            constexpr int V = 2 * S, kRep = 32 / V;
+            float v[V];
 #pragma unroll
-        for (int k = 0; k < S; ++k) {
+            for (int k = 0; k < S; ++k) {
+                v[2 * k] = p1[k];
+                v[2 * k + 1] = p2[k];
+            }
+            int o = 16;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                p1[k] += __shfl_xor_sync(0xffffffffu, p1[k], o);
-                p2[k] += __shfl_xor_sync(0xffffffffu, p2[k], o);
+            for (int n = V / 2; n >= 1; n >>= 1, o >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int j = 0; j < n; ++j) {
+                    const float give = up ? v[j] : v[j + n], keep = up ? v[j + n] : v[j];
+                    v[j] = keep + __shfl_xor_sync(0xffffffffu, give, o);
+                }
             }
-            if (lane == 0) {
-                s_warp[warp][2 * k] = p1[k];
-                s_warp[warp][2 * k + 1] = p2[k];
-            }
+#pragma unroll
+            for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+            if ((lane & (kRep - 1)) == 0) s_warp[warp][lane / kRep] = v[0];
         }
         __syncthreads(); // s_warp is complete, and every thread is done reading ring stage `stage`
         if (tid == 0 && i + kBwdStages < G) issue(i + kBwdStages);
+        const bool stat_thread = tid >= 32 && tid < 32 + 2 * S && i + kBwdStages < G;
+        float stat_next = 0.f; // in flight during the exchange and pass 2, stored at the end of the iteration
+        if (stat_thread) stat_next = stat_load(i + kBwdStages, tid - 32);
         // ---------------------------------------------------------------- exchange
         // This CTA's 2*S sums go to every CTA of the cluster (itself included); the receiver's mbarrier
         // counts the bytes. Two slots are enough: a peer sends group i+1 only after it has passed its
@@ -580,13 +621,24 @@ ln_relu_bwd_cluster_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict
                 uint32_t ow[4];
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    const f2 o = f2_fma(h[k][p], b2, f2_fma(w[k][p], rs2, a2)); // w*rstd - m1*rstd - h*m2*rstd
+                    f2 hh, ww;
+                    if constexpr (kPack) {
+                        hh = bf2_to_f2(h[k][p]);
+                        ww = bf2_to_f2(w[k][p]);
+                    } else {
+                        hh = h[k][p];
+                        ww = w[k][p];
+                    }
+                    const f2 o = f2_fma(hh, b2, f2_fma(ww, rs2, a2)); // w*rstd - m1*rstd - h*m2*rstd
                     dcb[p] = f2_add(dcb[p], o);
                     ow[p] = f2_to_bf2(o);
                 }
                 dx[smp * nvec + slot] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
         }
+        // every thread read s_stat[stage] before this iteration's __syncthreads; its next readers come
+        // after the next iteration's
+        if (stat_thread) s_stat[stage][tid - 32] = stat_next;
     }
 
     if (active) {
@@ -793,9 +845,16 @@ int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *
     const int nvec = D / 8;
     const int cs = (nvec + kBwdThreads - 1) / kBwdThreads; // CTAs per cluster: 2 / 4 / 8 for D = 4800 / 9600 / 19200
     if (cs > kMaxCluster) return INV_ERR_INVALID_ARG;      // D <= 20480
-    constexpr int S = 2;
     cudaStream_t st = (cudaStream_t)stream;
-    auto kern = res ? ln_relu_bwd_cluster_kernel<S, true> : ln_relu_bwd_cluster_kernel<S, false>;
+    // samples per cluster exchange: 4 without a residual input (INV_LN_BWD_S=2 selects 2, for A/B runs), 2 with
+    static int s_nores = -1;
+    if (s_nores < 0) {
+        const char *e = getenv("INV_LN_BWD_S");
+        s_nores = (e && e[0] == '2') ? 2 : 4;
+    }
+    const int S = res ? 2 : s_nores;
+    auto kern = res ? ln_relu_bwd_cluster_kernel<2, true>
+                    : (S == 4 ? ln_relu_bwd_cluster_kernel<4, false> : ln_relu_bwd_cluster_kernel<2, false>);
 
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -803,7 +862,7 @@ int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *
     attr[0].val.clusterDim.x = (unsigned)cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
-    const size_t smem = res ? bwd_cluster_smem<S, true>() : bwd_cluster_smem<S, false>();
+    const size_t smem = res ? bwd_cluster_smem<2, true>() : (S == 4 ? bwd_cluster_smem<4, false>() : bwd_cluster_smem<2, false>());
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return INV_ERR_CUDA;
     cfg.blockDim = dim3(kBwdThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
@@ -811,11 +870,12 @@ int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     // as many clusters as the GPU keeps resident at once (the work split is static per cluster)
-    static int resident[64][kMaxCluster + 1][2] = {};
+    static int resident[64][kMaxCluster + 1][3] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     int ncl = 0;
-    if (dev >= 0 && dev < 64) ncl = resident[dev][cs][res ? 1 : 0];
+    const int variant = res ? 1 : (S == 4 ? 2 : 0);
+    if (dev >= 0 && dev < 64) ncl = resident[dev][cs][variant];
     if (ncl == 0) {
         cfg.gridDim = dim3((unsigned)(cs * 64), 1, 1);
         if (cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg) != cudaSuccess || ncl <= 0) {
@@ -824,7 +884,7 @@ int inv_ln_relu_bwd(const void *dy, const void *x, const void *res, const void *
         }
         const int cap = 2 * sm_count_cached() / cs; // the partials buffer holds 2 * SMs parts
         if (ncl > cap) ncl = cap;
-        if (dev >= 0 && dev < 64) resident[dev][cs][res ? 1 : 0] = ncl;
+        if (dev >= 0 && dev < 64) resident[dev][cs][variant] = ncl;
     }
     const int64_t groups = (B + S - 1) / S;
     if (ncl > groups) ncl = (int)groups;
