@@ -169,6 +169,25 @@ int inv_step_host(inv_sim *sim, const int8_t *a_p1, const int8_t *a_p2, void *ob
                   int32_t *episode_steps, double *episode_return);
 int inv_reset_host(inv_sim *sim, void *obs_p1, float *extra_p1, void *obs_p2, float *extra_p2);
 
+/* One episode that ended in a step: what the trainer reads at training.py:140-151 (episode_return,
+ * episode_steps, win) for the envs whose done flag is set. */
+typedef struct {
+    int64_t env;            /* local env index, ascending within a step */
+    double episode_return;  /* info["episode_return"], env_wrappers.py:442 */
+    int32_t episode_steps;  /* info["episode_steps"],  env_wrappers.py:441 */
+    uint32_t info;          /* INV_INFO_* bits (win / lose / landed_hit / got_hit) */
+} inv_episode_event;
+
+/* The step as a trainer with a GPU-resident policy consumes it: actions come from host memory, the
+ * observations -- grid and extra -- stay on the device (inv_buffer), reward / done / info arrive
+ * dense (any may be NULL), and the episodes that ended in this step arrive as a compact list in env
+ * order: *n_events records in events[0 .. capacity). 6 bytes per env plus 24 per finished episode
+ * cross the bus instead of inv_step_host's 34 per env. capacity >= n_envs can never overflow; if
+ * fewer fit, *n_events still holds the true count and INV_ERR_INVALID_ARG is returned (the step has
+ * been taken). Same argument errors as inv_step_host. */
+int inv_step_host_events(inv_sim *sim, const int8_t *a_p1, const int8_t *a_p2, float *reward, uint8_t *done,
+                         uint8_t *info, inv_episode_event *events, int64_t capacity, int64_t *n_events);
+
 /* How inv_step_host delivers float32 observations to host memory. nthreads = 0: one plain
  * device-to-host copy (PCIe-bound, about 7.2 KB per env). nthreads > 0 (default: the host's
  * hardware threads, at most 32): the kernel also emits each observation as its packed 1800-bit

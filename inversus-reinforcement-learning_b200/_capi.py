@@ -43,6 +43,11 @@ STATE_DTYPE = np.dtype([
     ("episode", np.uint32), ("episode_return", np.float64)], align=True)
 assert STATE_DTYPE.itemsize == C.sizeof(EnvState), (STATE_DTYPE.itemsize, C.sizeof(EnvState))
 
+# numpy mirror of inv_episode_event (one finished episode, inv_step_host_events)
+EVENT_DTYPE = np.dtype([("env", np.int64), ("episode_return", np.float64), ("episode_steps", np.int32),
+                        ("info", np.uint32)], align=True)
+assert EVENT_DTYPE.itemsize == 24
+
 # every symbol include/inversus_b200.h declares: (restype, argtypes)
 _P = C.POINTER
 SYMBOLS = {
@@ -56,6 +61,7 @@ SYMBOLS = {
     "inv_reset_envs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "inv_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "inv_step_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 11),
+    "inv_step_host_events": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, _P(C.c_int64)]),
     "inv_reset_host": (C.c_int, [C.c_void_p] + [C.c_void_p] * 4),
     "inv_set_host_path": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "inv_get_host_path": (C.c_int, [C.c_void_p, _P(C.c_int), _P(C.c_double), _P(C.c_double), _P(C.c_double)]),

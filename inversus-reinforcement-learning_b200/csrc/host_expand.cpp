@@ -111,6 +111,45 @@ void expand_f32(const uint32_t *bits, float *dst, int64_t lo, int64_t hi, int nt
     for (auto &x : th) x.join();
 }
 
+// Action ids on their way to the device: one pass copies them into the pinned staging buffer and
+// checks 0 <= id <= 12 (discrete_to_action's ValueError, env_wrappers.py:66). Returns true if an id
+// is out of range. AVX2: max_epu8(v, 12) differs from 12 exactly for the bytes above 12 (negative
+// int8 ids are large unsigned bytes).
+__attribute__((target("avx2"))) static bool stage_ids_avx2(int8_t *dst, const int8_t *src, int64_t n)
+{
+    const __m256i twelve = _mm256_set1_epi8(12);
+    __m256i bad0 = _mm256_setzero_si256(), bad1 = _mm256_setzero_si256();
+    int64_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 32));
+        _mm256_storeu_si256(reinterpret_cast<__m256i *>(dst + i), a);
+        _mm256_storeu_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
+        bad0 = _mm256_or_si256(bad0, _mm256_xor_si256(_mm256_max_epu8(a, twelve), twelve));
+        bad1 = _mm256_or_si256(bad1, _mm256_xor_si256(_mm256_max_epu8(b, twelve), twelve));
+    }
+    unsigned bad = _mm256_testz_si256(_mm256_or_si256(bad0, bad1), _mm256_set1_epi8(-1)) ? 0u : 1u;
+    for (; i < n; ++i) {
+        const int8_t v = src[i];
+        dst[i] = v;
+        bad |= (unsigned)((uint8_t)v > 12);
+    }
+    return bad != 0;
+}
+
+bool stage_action_ids(int8_t *dst, const int8_t *src, int64_t n)
+{
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) return stage_ids_avx2(dst, src, n);
+    unsigned bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int8_t v = src[i];
+        dst[i] = v;
+        bad |= (unsigned)((uint8_t)v > 12);
+    }
+    return bad != 0;
+}
+
 int hardware_threads()
 {
     unsigned n = std::thread::hardware_concurrency();

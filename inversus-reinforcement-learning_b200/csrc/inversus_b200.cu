@@ -19,6 +19,7 @@ using namespace inv;
 namespace inv_host { // host_expand.cpp
 void expand_f32(const uint32_t *bits, float *dst, int64_t lo, int64_t hi, int nthreads);
 int hardware_threads();
+bool stage_action_ids(int8_t *dst, const int8_t *src, int64_t n);
 } // namespace inv_host
 
 struct inv_sim {
@@ -54,6 +55,12 @@ struct inv_sim {
     uint4 *d_bits[2];
     uint32_t *h_bits[2];
     double last_dma_s, last_expand_s;
+    // inv_step_host_events: compact list of the episodes that ended in the step
+    char *d_events;         // [16-byte header: int64 count][n records of inv_episode_event]
+    int32_t *d_ev_counts;   // finished episodes per block of kEvBlockEnvs envs
+    int64_t *h_ev_count;    // pinned landing slot of the header
+    int64_t ev_guess;       // records fetched together with the header (1.5 x the last count)
+    cudaEvent_t ev_events;
 };
 
 static thread_local char g_err[512] = "";
@@ -104,6 +111,109 @@ __global__ void gae_kernel(const float *__restrict__ reward, const float *__rest
         adv[k] = last;                                                         // :151
         ret[k] = __fadd_rn(last, v);                                           // :154
         next_v = v;
+    }
+}
+
+// ---- finished-episode list (inv_step_host_events) -----------------------------------------------
+// Two small launches over the done flags, deterministic and in env order: blocks of kEvBlockEnvs envs
+// count their finished episodes, then every block sums the counts before it, scans its own threads
+// and writes its records. 16 done bytes per thread and load.
+constexpr int kEvThreads = 256, kEvPerThread = 16, kEvBlockEnvs = kEvThreads * kEvPerThread;
+constexpr size_t kEvHeaderBytes = 16;
+static_assert(sizeof(inv_episode_event) == 24, "inv_episode_event is 24 bytes in the ABI");
+
+__device__ __forceinline__ uint32_t done_mask16(const uint8_t *__restrict__ done, int64_t i, int64_t n)
+{
+    uint32_t m = 0;
+    if (i + kEvPerThread <= n) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(done + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) m |= ((w[q] >> (8 * b)) & 0xFFu) ? 1u << (4 * q + b) : 0u;
+    } else {
+        for (int k = 0; k < kEvPerThread; ++k)
+            if (i + k < n && done[i + k]) m |= 1u << k;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(kEvThreads) episode_count_kernel(const uint8_t *__restrict__ done, int64_t n,
+                                                                    int32_t *__restrict__ block_counts)
+{
+    const int64_t i = (int64_t)blockIdx.x * kEvBlockEnvs + (int64_t)threadIdx.x * kEvPerThread;
+    int c = i < n ? __popc(done_mask16(done, i, n)) : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ int s_c[kEvThreads / 32];
+    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kEvThreads / 32; ++w) t += s_c[w];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kEvThreads)
+episode_write_kernel(const uint8_t *__restrict__ done, const uint8_t *__restrict__ info,
+                     const int32_t *__restrict__ ep_steps, const double *__restrict__ ep_return, int64_t n,
+                     const int32_t *__restrict__ block_counts, int64_t *__restrict__ header,
+                     inv_episode_event *__restrict__ events)
+{
+    __shared__ long long s_part[kEvThreads / 32];
+    __shared__ int s_w[kEvThreads / 32];
+    __shared__ long long s_base;
+    // records of the blocks before this one (and, in the last block, the grand total for the header)
+    long long before = 0, total = 0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kEvThreads) {
+        const int c = block_counts[b];
+        total += c;
+        if (b < (int)blockIdx.x) before += c;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        before += __shfl_xor_sync(0xffffffffu, before, o);
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) s_part[warp] = before;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < kEvThreads / 32; ++w) t += s_part[w];
+        s_base = t;
+    }
+    __syncthreads();
+    if (blockIdx.x == gridDim.x - 1) { // total: same reduction once more, by the last block only
+        if (lane == 0) s_part[warp] = total;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long t = 0;
+            for (int w = 0; w < kEvThreads / 32; ++w) t += s_part[w];
+            header[0] = t;
+        }
+    }
+    const int64_t i = (int64_t)blockIdx.x * kEvBlockEnvs + (int64_t)threadIdx.x * kEvPerThread;
+    const uint32_t m = i < n ? done_mask16(done, i, n) : 0u;
+    const int c = __popc(m);
+    int incl = c; // inclusive scan of the per-thread counts: warp, then across the block's warps
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_w[w];
+    long long pos = s_base + woff + incl - c;
+    for (uint32_t mm = m; mm; mm &= mm - 1) {
+        const int64_t e = i + (__ffs(mm) - 1);
+        inv_episode_event r;
+        r.env = e;
+        r.episode_return = ep_return[e];
+        r.episode_steps = ep_steps[e];
+        r.info = info[e];
+        events[pos++] = r;
     }
 }
 
@@ -439,6 +549,10 @@ int inv_destroy(inv_sim *s)
         if (s->d_bits[v]) cudaFree(s->d_bits[v]);
         if (s->h_bits[v]) cudaFreeHost(s->h_bits[v]);
     }
+    if (s->d_events) cudaFree(s->d_events);
+    if (s->d_ev_counts) cudaFree(s->d_ev_counts);
+    if (s->h_ev_count) cudaFreeHost(s->h_ev_count);
+    if (s->ev_events) cudaEventDestroy(s->ev_events);
     if (s->host_stream) cudaStreamDestroy(s->host_stream);
     delete s;
     return INV_OK;
@@ -629,61 +743,70 @@ static int ensure_bits_staging(inv_sim *s, bool p2)
     return INV_OK;
 }
 
-int inv_step_host(inv_sim *s, const int8_t *a1, const int8_t *a2, void *obs_p1, float *extra_p1, void *obs_p2,
-                  float *extra_p2, float *reward, uint8_t *done, uint8_t *info, int32_t *episode_steps,
-                  double *episode_return)
+// What every host-buffer step starts with: the reference's argument errors, then the action ids
+// host -> pinned staging -> device on the handle's own stream.
+static int begin_host_step(inv_sim *s, const int8_t *a1, const int8_t *a2, const char *who)
 {
-    if (!s || !a1) return fail(INV_ERR_INVALID_ARG, "inv_step_host: null argument");
-    if (!s->was_reset) return fail(INV_ERR_NOT_RESET, "inv_step_host before inv_reset");
+    if (!s || !a1) return fail(INV_ERR_INVALID_ARG, "%s: null argument", who);
+    if (!s->was_reset) return fail(INV_ERR_NOT_RESET, "%s before inv_reset", who);
     const bool selfplay = s->cfg.mode == INV_MODE_SELFPLAY;
     if (selfplay && !a2) return fail(INV_ERR_INVALID_ARG, "opponent_policy required for selfplay mode");
-    if (obs_p1 && !s->obs1) return fail(INV_ERR_INVALID_ARG, "this handle keeps no observation tensor (INV_OBS_NONE)");
-    if (obs_p2 && !s->obs2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
-    if (extra_p2 && !s->extra2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
     const int64_t n = s->n;
-    // discrete_to_action raises before anything is stepped (env_wrappers.py:302, :66); one
-    // branch-free pass over the ids (vectorised by the compiler), then report
-    {
-        unsigned bad = 0;
-        for (int64_t i = 0; i < n; ++i) bad |= (unsigned)((uint8_t)a1[i] > 12);
-        if (selfplay)
-            for (int64_t i = 0; i < n; ++i) bad |= (unsigned)((uint8_t)a2[i] > 12);
-        if (bad) return fail(INV_ERR_INVALID_ACTION, "Invalid action_id: must be 0-12");
-    }
-    DeviceGuard g(s->cfg.device);
     int rc = ensure_host_staging(s);
     if (rc != INV_OK) return rc;
-    const bool expand = use_host_expand(s, obs_p1, obs_p2);
-    if (expand && (rc = ensure_bits_staging(s, obs_p2 != nullptr)) != INV_OK) return rc;
-    cudaStream_t ks = s->host_stream, cs = s->copy_stream;
+    // discrete_to_action raises before anything is stepped (env_wrappers.py:302, :66): the ids are
+    // checked in the same pass that moves them into the pinned staging buffer, and nothing has been
+    // enqueued when the error is reported
+    bool bad = inv_host::stage_action_ids(s->h_a1, a1, n);
+    if (selfplay) bad |= inv_host::stage_action_ids(s->h_a2, a2, n);
+    if (bad) return fail(INV_ERR_INVALID_ACTION, "Invalid action_id: must be 0-12");
     if ((rc = order_host_stream(s)) != INV_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->d_a1, s->h_a1, (size_t)n, cudaMemcpyHostToDevice, s->host_stream));
+    if (selfplay) CUDA_TRY(cudaMemcpyAsync(s->d_a2, s->h_a2, (size_t)n, cudaMemcpyHostToDevice, s->host_stream));
+    return INV_OK;
+}
 
-    // action ids travel host -> pinned staging -> device on the handle's own stream
-    memcpy(s->h_a1, a1, (size_t)n);
-    CUDA_TRY(cudaMemcpyAsync(s->d_a1, s->h_a1, (size_t)n, cudaMemcpyHostToDevice, ks));
-    if (selfplay) {
-        memcpy(s->h_a2, a2, (size_t)n);
-        CUDA_TRY(cudaMemcpyAsync(s->d_a2, s->h_a2, (size_t)n, cudaMemcpyHostToDevice, ks));
-    }
-
+// Env ranges of the pipelined host step; returns the number of chunks, bounds[0 .. chunks] filled.
+static int host_chunk_bounds(int64_t n, bool with_obs, bool single, int64_t *bounds)
+{
     int nchunks = (int)(n / kHostChunkMinEnvs);
     nchunks = nchunks < 1 ? 1 : (nchunks > kMaxHostChunks ? kMaxHostChunks : nchunks);
-    if (!(obs_p1 || obs_p2) && nchunks > 4) nchunks = 4; // small outputs only: fewer, larger copies
+    if (!with_obs && nchunks > 4) nchunks = 4; // small outputs only: fewer, larger copies
     if (const char *e = getenv("INV_HOST_CHUNKS")) { // experiments (profiles/)
         const int v = atoi(e);
         if (v >= 1 && v <= kMaxHostChunks && (int64_t)v <= n / 256) nchunks = v;
     }
-    if (s->h_small) nchunks = 1;
+    if (single) nchunks = 1;
     const int64_t per = ((n + nchunks - 1) / nchunks + 255) & ~(int64_t)255;
     // small outputs only: what is not overlapped is the LAST chunk's copy, so the chunks shrink
     // towards the end (3 : 3 : 1 : 1)
-    int64_t bounds[kMaxHostChunks + 1];
-    const bool tapered = !(obs_p1 || obs_p2) && nchunks == 4;
+    const bool tapered = !with_obs && nchunks == 4;
     for (int c = 0; c <= nchunks; ++c) {
         int64_t b = tapered ? (n * (c == 0 ? 0 : c == 1 ? 3 : c == 2 ? 6 : c == 3 ? 7 : 8) / 8) & ~(int64_t)255
                             : (int64_t)c * per;
         bounds[c] = (c == nchunks || b > n) ? n : b;
     }
+    return nchunks;
+}
+
+int inv_step_host(inv_sim *s, const int8_t *a1, const int8_t *a2, void *obs_p1, float *extra_p1, void *obs_p2,
+                  float *extra_p2, float *reward, uint8_t *done, uint8_t *info, int32_t *episode_steps,
+                  double *episode_return)
+{
+    if (!s) return fail(INV_ERR_INVALID_ARG, "inv_step_host: null argument");
+    if (obs_p1 && !s->obs1) return fail(INV_ERR_INVALID_ARG, "this handle keeps no observation tensor (INV_OBS_NONE)");
+    if (obs_p2 && !s->obs2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
+    if (extra_p2 && !s->extra2) return fail(INV_ERR_INVALID_ARG, "P2 view was not enabled (INV_FLAG_P2_VIEW)");
+    DeviceGuard g(s->cfg.device);
+    int rc = begin_host_step(s, a1, a2, "inv_step_host");
+    if (rc != INV_OK) return rc;
+    const int64_t n = s->n;
+    const bool selfplay = s->cfg.mode == INV_MODE_SELFPLAY;
+    const bool expand = use_host_expand(s, obs_p1, obs_p2);
+    if (expand && (rc = ensure_bits_staging(s, obs_p2 != nullptr)) != INV_OK) return rc;
+    cudaStream_t ks = s->host_stream, cs = s->copy_stream;
+    int64_t bounds[kMaxHostChunks + 1];
+    const int nchunks = host_chunk_bounds(n, obs_p1 || obs_p2, s->h_small != nullptr, bounds);
     const SmallOut so = {extra_p1, extra_p2, reward, done, info, episode_steps, episode_return};
     const size_t env_bytes = (size_t)INV_OBS_ELEMS * obs_elem_bytes(s->cfg.obs_dtype);
     void *dst[2] = {obs_p1, obs_p2};
@@ -754,6 +877,104 @@ int inv_step_host(inv_sim *s, const int8_t *a1, const int8_t *a2, void *obs_p1, 
             f = f < 0.0 ? 0.0 : (f > 0.9 ? 0.9 : f);
             s->dma_frac = 0.5 * s->dma_frac + 0.5 * f;
         }
+    }
+    return INV_OK;
+}
+
+// The trainer's view of a step (training.py:140-151): observations -- grid AND extra -- are consumed on
+// the GPU; the host wants reward / done / info per env and the statistics of the episodes that just
+// ended. Dense: 6 bytes per env. Sparse: one 24-byte record per finished episode, in env order,
+// fetched together with its count (1.5 x the previous step's count travels with the header; a second
+// copy follows only if more episodes ended than that).
+static int ensure_event_buffers(inv_sim *s)
+{
+    if (s->d_events) return INV_OK;
+    const size_t nblocks = ((size_t)s->n + kEvBlockEnvs - 1) / kEvBlockEnvs;
+    const size_t ev_bytes = kEvHeaderBytes + (size_t)s->n * sizeof(inv_episode_event);
+    CUDA_TRY(cudaMalloc((void **)&s->d_events, ev_bytes));
+    CUDA_TRY(cudaMemsetAsync(s->d_events, 0, ev_bytes, s->host_stream)); // the prefix copy may read past the count
+    CUDA_TRY(cudaMalloc((void **)&s->d_ev_counts, nblocks * sizeof(int32_t)));
+    CUDA_TRY(cudaMallocHost((void **)&s->h_ev_count, sizeof(int64_t)));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_events, cudaEventDisableTiming));
+    s->ev_guess = 1024;
+    return INV_OK;
+}
+
+int inv_step_host_events(inv_sim *s, const int8_t *a1, const int8_t *a2, float *reward, uint8_t *done,
+                         uint8_t *info, inv_episode_event *events, int64_t capacity, int64_t *n_events)
+{
+    if (!s || !events || !n_events || capacity < 0)
+        return fail(INV_ERR_INVALID_ARG, "inv_step_host_events: null handle, events or n_events, or negative capacity");
+    DeviceGuard g(s->cfg.device);
+    static const bool trace = getenv("INV_HOST_TRACE") != nullptr; // stderr: where a call's wall time goes
+    const auto t_in = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (trace)
+            fprintf(stderr, "[inv_step_host_events] %-22s %8.1f us\n", what,
+                    std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_in).count());
+    };
+    int rc = begin_host_step(s, a1, a2, "inv_step_host_events");
+    if (rc != INV_OK) return rc;
+    lap("ids checked + staged");
+    if ((rc = ensure_event_buffers(s)) != INV_OK) return rc;
+    const int64_t n = s->n;
+    const bool selfplay = s->cfg.mode == INV_MODE_SELFPLAY;
+    cudaStream_t ks = s->host_stream, cs = s->copy_stream;
+    int64_t bounds[kMaxHostChunks + 1];
+    const int nchunks = host_chunk_bounds(n, false, false, bounds);
+    int used = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t first = bounds[c], count = bounds[c + 1] - first;
+        if (first >= n || count <= 0) break;
+        if ((rc = step_impl(s, s->d_a1, selfplay ? s->d_a2 : nullptr, ks, nullptr, nullptr, first, count)) != INV_OK) return rc;
+        CUDA_TRY(cudaEventRecord(s->ev_kernel[c], ks));
+        used = c + 1;
+    }
+    {   // the finished-episode list, once the whole done array is in place
+        const unsigned nblocks = (unsigned)((n + kEvBlockEnvs - 1) / kEvBlockEnvs);
+        int64_t *header = reinterpret_cast<int64_t *>(s->d_events);
+        inv_episode_event *recs = reinterpret_cast<inv_episode_event *>(s->d_events + kEvHeaderBytes);
+        episode_count_kernel<<<nblocks, kEvThreads, 0, ks>>>(s->done, n, s->d_ev_counts);
+        episode_write_kernel<<<nblocks, kEvThreads, 0, ks>>>(s->done, s->info, s->ep_steps, s->ep_return, n,
+                                                             s->d_ev_counts, header, recs);
+        CUDA_TRY(cudaGetLastError());
+        s->launches += 2;
+        CUDA_TRY(cudaEventRecord(s->ev_events, ks));
+    }
+    for (int c = 0; c < used; ++c) { // dense outputs follow chunk by chunk on the copy stream
+        const size_t f = (size_t)bounds[c], cnt = (size_t)(bounds[c + 1] - bounds[c]);
+        CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_kernel[c], 0));
+        if (reward) CUDA_TRY(cudaMemcpyAsync(reward + f, s->reward + f, cnt * 4, cudaMemcpyDeviceToHost, cs));
+        if (done) CUDA_TRY(cudaMemcpyAsync(done + f, s->done + f, cnt, cudaMemcpyDeviceToHost, cs));
+        if (info) CUDA_TRY(cudaMemcpyAsync(info + f, s->info + f, cnt, cudaMemcpyDeviceToHost, cs));
+    }
+    const char *recs = s->d_events + kEvHeaderBytes;
+    const int64_t guess = s->ev_guess < capacity ? s->ev_guess : capacity;
+    CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_events, 0));
+    CUDA_TRY(cudaMemcpyAsync(s->h_ev_count, s->d_events, sizeof(int64_t), cudaMemcpyDeviceToHost, cs));
+    if (guess > 0)
+        CUDA_TRY(cudaMemcpyAsync(events, recs, (size_t)guess * sizeof(inv_episode_event), cudaMemcpyDeviceToHost, cs));
+    lap("all work enqueued");
+    if (trace) {
+        for (int c = 0; c < used; ++c) {
+            cudaEventSynchronize(s->ev_kernel[c]);
+            lap("a chunk's kernel done");
+        }
+        cudaEventSynchronize(s->ev_events);
+        lap("event list built");
+    }
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    lap("copies landed");
+    const int64_t count = *s->h_ev_count;
+    *n_events = count;
+    s->ev_guess = count + count / 4 < 1024 ? 1024 : count + count / 4;
+    if (count > capacity)
+        return fail(INV_ERR_INVALID_ARG, "inv_step_host_events: more episodes ended than the events buffer holds "
+                                         "(the step has been taken; capacity >= num_envs never overflows)");
+    if (count > guess) {
+        CUDA_TRY(cudaMemcpyAsync(events + guess, recs + (size_t)guess * sizeof(inv_episode_event),
+                                 (size_t)(count - guess) * sizeof(inv_episode_event), cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaStreamSynchronize(cs));
     }
     return INV_OK;
 }

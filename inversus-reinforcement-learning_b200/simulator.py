@@ -197,6 +197,53 @@ class BatchedInversus:
                                             p("obs_p2"), p("extra_p2"), p("reward"), p("done"), p("info"),
                                             p("episode_steps"), p("episode_return")))
 
+    def step_host_events(self, a1: np.ndarray, a2: Optional[np.ndarray], out: dict) -> np.ndarray:
+        """inv_step_host_events: the step as a trainer with a GPU-resident policy consumes it
+        (training.py:140-151). Observations -- grid and extra -- stay on the device; `out` maps
+        reward/done/info to preallocated arrays (any may be missing) and "events" to an array of
+        _capi.EVENT_DTYPE records. Returns the view of `out["events"]` holding the episodes that
+        ended in this step, in env order."""
+        def p(k):
+            v = out.get(k)
+            return None if v is None else v.ctypes.data_as(C.c_void_p)
+        a1 = np.ascontiguousarray(a1, np.int8)
+        a2p = None
+        if a2 is not None:
+            a2 = np.ascontiguousarray(a2, np.int8)
+            a2p = a2.ctypes.data_as(C.c_void_p)
+        if a1.size != self.num_envs:
+            raise ValueError("action_ids has the wrong length")
+        ev = out["events"]
+        if ev.dtype != _capi.EVENT_DTYPE or not ev.flags.c_contiguous:
+            raise ValueError("out['events'] must be a contiguous array of _capi.EVENT_DTYPE")
+        count = C.c_int64(0)
+        _capi.check(self._lib.inv_step_host_events(self._h.ptr, a1.ctypes.data_as(C.c_void_p), a2p, p("reward"),
+                                                   p("done"), p("info"), ev.ctypes.data_as(C.c_void_p), ev.size,
+                                                   C.byref(count)))
+        return ev[:count.value]
+
+    def host_event_buffers(self, pinned: bool = True, capacity: Optional[int] = None) -> dict:
+        """Output buffers for step_host_events (page-locked by default); capacity defaults to num_envs,
+        which can never overflow."""
+        n = self.num_envs
+        cap = n if capacity is None else int(capacity)
+        spec = {"reward": (n, np.float32), "done": (n, np.uint8), "info": (n, np.uint8)}
+        out = {}
+        for k, (count, dt) in spec.items():
+            if pinned:
+                t = torch.empty(count, dtype=torch.from_numpy(np.zeros(0, dt)).dtype, pin_memory=True)
+                out[k] = t.numpy()
+                out.setdefault("_pins", []).append(t)
+            else:
+                out[k] = np.empty(count, dt)
+        if pinned:
+            raw = torch.empty(max(cap, 1) * _capi.EVENT_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+            out["_pins"].append(raw)
+            out["events"] = raw.numpy().view(_capi.EVENT_DTYPE)[:cap]
+        else:
+            out["events"] = np.empty(cap, _capi.EVENT_DTYPE)
+        return out
+
     def reset_host(self, out: dict) -> None:
         def p(k):
             v = out.get(k)

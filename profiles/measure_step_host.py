@@ -30,3 +30,26 @@ for what, bufs, steps in (("small outputs only", small, 30), ("full fp32 observa
             sim.step_host(acts[k % 4], None, bufs)
         dt = (time.perf_counter() - t0) / steps
         print(f"{what}: chunks={chunks}  {dt * 1e3:.3f} ms/step  {n / dt / 1e6:.1f} M env-steps/s  {sim.host_path()}", flush=True)
+
+# the trainer's view: reward / done / info dense + the finished episodes as a compact list
+os.environ.pop("INV_HOST_CHUNKS", None)
+ev = sim.host_event_buffers(pinned=True)
+dense3 = {k: small[k] for k in ("reward", "done", "info")}
+for what, fn in (("reward/done/info only (no extra, no episode stats)", lambda a: sim.step_host(a, None, dense3)),
+                 ("reward/done/info + finished-episode list", lambda a: sim.step_host_events(a, None, ev))):
+    for chunks in (0, 1, 2, 4):
+        if chunks:
+            os.environ["INV_HOST_CHUNKS"] = str(chunks)
+        else:
+            os.environ.pop("INV_HOST_CHUNKS", None)
+        for k in range(20):
+            fn(acts[k % 4])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cnt = 0
+        for k in range(100):
+            r = fn(acts[k % 4])
+            cnt += 0 if r is None else len(r)
+        dt = (time.perf_counter() - t0) / 100
+        print(f"{what}: chunks={chunks or 'default'}  {dt * 1e3:.3f} ms/step  {n / dt / 1e6:.1f} M env-steps/s  "
+              f"finished episodes per step {cnt / 100:.0f}", flush=True)

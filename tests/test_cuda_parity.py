@@ -192,6 +192,72 @@ def test_host_buffer_paths_deliver_identical_observations(mode):
     assert 0.0 <= sims["auto"][0].host_path()["dma_fraction"] <= 0.9
 
 
+@pytest.mark.parametrize("n,chunks", [(37, 1), (4096 * 3 + 5, 1), (70001, 4), (70001, 3)])
+def test_host_step_with_episode_events_matches_the_dense_outputs(n, chunks, monkeypatch):
+    """inv_step_host_events (the trainer's view, training.py:140-151): reward / done / info dense and
+    the finished episodes as a compact list. The list must be exactly the dense episode_steps /
+    episode_return / info of the envs whose done flag is set, in env order; the device state and the
+    observations left on the device must equal the dense call's. Short episodes (max 12 steps) make
+    the list outgrow the prefix that travels with the count (second-copy path) from step 12 on."""
+    import torch
+    from inversus_b200 import BatchedInversus, _capi
+    monkeypatch.setenv("INV_HOST_STAGED_MAX", "0")
+    rs = np.random.RandomState(11)
+    for mode in ("dummy", "selfplay"):
+        monkeypatch.delenv("INV_HOST_CHUNKS", raising=False)
+        ref = BatchedInversus(n, mode, "hard", 12, seed=9, auto_reset=True)
+        got = BatchedInversus(n, mode, "hard", 12, seed=9, auto_reset=True)
+        ref.reset()
+        got.reset()
+        ro = ref.host_buffers(pinned=False)
+        eo = got.host_event_buffers(pinned=(mode == "dummy"))
+        seen = 0
+        for t in range(30):
+            a1 = rs.randint(0, 13, n).astype(np.int8)
+            a2 = rs.randint(0, 13, n).astype(np.int8) if mode == "selfplay" else None
+            monkeypatch.delenv("INV_HOST_CHUNKS", raising=False)
+            ref.step_host(a1, a2, ro)
+            if chunks > 1:
+                monkeypatch.setenv("INV_HOST_CHUNKS", str(chunks))
+            eo["events"][:] = np.zeros(1, _capi.EVENT_DTYPE)[0]
+            ev = got.step_host_events(a1, a2, eo)
+            for k in ("reward", "done", "info"):
+                assert np.array_equal(eo[k], ro[k]), (mode, t, k)
+            idx = np.flatnonzero(ro["done"])
+            assert ev.shape[0] == idx.size, (mode, t)
+            assert np.array_equal(ev["env"], idx)
+            assert np.array_equal(ev["episode_steps"], ro["episode_steps"][idx])
+            assert np.array_equal(ev["episode_return"], ro["episode_return"][idx])   # binary64, bit for bit
+            assert np.array_equal(ev["info"], ro["info"][idx].astype(np.uint32))
+            seen += idx.size
+            assert torch.equal(got.packed_state, ref.packed_state)
+            assert torch.equal(got.obs, ref.obs) and torch.equal(got.extra, ref.extra)
+        assert seen > n                     # every env finished at least twice on average
+        assert got.poll_status() == 0
+        # a list that does not fit: the true count comes back with the error
+        small = dict(eo)
+        small["events"] = np.zeros(1, _capi.EVENT_DTYPE)
+        for _ in range(12):
+            a1 = np.zeros(n, np.int8)
+            try:
+                got.step_host_events(a1, a1 if mode == "selfplay" else None, small)
+            except ValueError as e:
+                assert "events buffer" in str(e)
+                break
+        else:
+            raise AssertionError("no overflow reported within one episode length")
+        before = got.packed_state.clone()
+        for pos, val in ((n - 1, 13), (5, -1), (n // 2, 127)):   # vector body and scalar tail of the id check
+            with pytest.raises(ValueError):
+                bad = np.zeros(n, np.int8)
+                bad[pos] = val
+                got.step_host_events(np.zeros(n, np.int8) if mode == "selfplay" else bad,
+                                     bad if mode == "selfplay" else None, eo)
+        assert torch.equal(got.packed_state, before)             # nothing was stepped
+        ref.close()
+        got.close()
+
+
 @pytest.mark.parametrize("chunks", [2, 3, 4, 8])
 def test_chunked_host_pipeline_delivers_the_same_bytes(chunks, monkeypatch):
     """inv_step_host cuts large batches into env chunks (kernel c+1 overlaps the copies of chunk c,
