@@ -605,6 +605,33 @@ def main():
             "obs_stay_on_device": run_e2e(0, 0.0, False, warm=1),
         }
         e2e_variants["obs_stay_on_device"]["note"] = "actions up; reward/done/info/extra/episode stats down; observations consumed on the GPU"
+
+        # the trainer's loop (training.py:140-151) with a GPU-resident policy: grid AND extra stay on the
+        # device, reward/done/info arrive dense, episode statistics only for the episodes that ended
+        def run_events():
+            eo = esim.host_event_buffers(pinned=True)
+            steps = max(50, 10 * args.e2e_steps)
+            for k in range(10):
+                esim.step_host_events(h_acts[k % 4], None if h_acts2 is None else h_acts2[k % 4], eo)
+            barrier()
+            finished = 0
+            t0 = time.perf_counter()
+            for k in range(steps):
+                finished += len(esim.step_host_events(h_acts[k % 4], None if h_acts2 is None else h_acts2[k % 4], eo))
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            per_step = finished / steps
+            return {"value": ne * world * steps / dt, "unit": UNIT, "h2d_bytes_per_step": ne * views,
+                    "d2h_bytes_per_step": int(ne * 6 + 8 + 24 * per_step), "steps": steps, "envs_per_gpu": ne,
+                    "ms_per_step": 1e3 * dt / steps, "finished_episodes_per_step": per_step,
+                    "api": "inv_step_host_events (C ABI)",
+                    "note": "actions up; reward/done/info dense + one 24-byte record per finished episode down; "
+                            "observations (grid and extra) consumed on the GPU"}
+        e2e_variants["obs_stay_on_device_episode_events"] = run_events()
         esim.set_host_path(host_threads, -1.0)
 
     # ------------------------------------------------------------------ optional sweep (stderr)
