@@ -55,6 +55,9 @@ def test_b200_arm_line():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 16384 and e["d2h_bytes_per_step"] > 16384 * 256
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert d["config"]["preroll_steps"] == 500 + 100 - 3       # timed steps lie past the first episode timeout
+    ev = d["e2e_variants"]["obs_stay_on_device_episode_events"]
+    assert ev["value"] > 0 and ev["d2h_bytes_per_step"] < d["e2e_variants"]["obs_stay_on_device"]["d2h_bytes_per_step"]
 
 
 @pytest.mark.gpu
