@@ -597,13 +597,12 @@ struct __align__(32) uint8v { uint4 lo, hi; }; // one 32-byte store (st.global.v
 template <> struct ObsFmt<INV_OBS_F32> {  // 1800 f32 = 225 x 32 B, 8 bits per chunk
     static constexpr int kChunks = 225, kBits = 8;
     typedef uint8v chunk_t;
+    template <int K> static __device__ __forceinline__ uint32_t one(uint32_t b) { return (b & (1u << K)) * (0x3F800000u >> K); }
     static __device__ __forceinline__ chunk_t expand(uint32_t b)
     {
-        chunk_t c;
-        c.lo = make_uint4((b & 1u) ? 0x3F800000u : 0u, (b & 2u) ? 0x3F800000u : 0u,
-                          (b & 4u) ? 0x3F800000u : 0u, (b & 8u) ? 0x3F800000u : 0u);
-        c.hi = make_uint4((b & 16u) ? 0x3F800000u : 0u, (b & 32u) ? 0x3F800000u : 0u,
-                          (b & 64u) ? 0x3F800000u : 0u, (b & 128u) ? 0x3F800000u : 0u);
+        chunk_t c; // bit k -> 1.0f or 0.0f in two instructions: isolate (LOP3), scale by 0x3F800000 >> k (IMAD, exact for k <= 23)
+        c.lo = make_uint4(one<0>(b), one<1>(b), one<2>(b), one<3>(b));
+        c.hi = make_uint4(one<4>(b), one<5>(b), one<6>(b), one<7>(b));
         return c;
     }
 };
