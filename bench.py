@@ -386,7 +386,7 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["steps"], "warmup": W, "ms_per_step": 1e3 * r["seconds"] / max(r["steps"], 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, max(args.gpus, 1)),   # the B200 arm's config at this N, key for key
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": kind, "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "c_port": port_line,
@@ -398,6 +398,11 @@ def reference_arm(args):
     return 0
 
 
+def resolved_preroll(args):
+    """Untimed steps before the warm-up (a function of the flags only, so both arms print the same config)."""
+    return args.preroll if args.preroll >= 0 else max(0, args.max_episode_steps + 100 - max(args.warmup, 3))
+
+
 def workload_config(args, world):
     return {
         "workload": f"random-action fused step+obs, vs_{args.mode} {args.difficulty}, "
@@ -406,7 +411,7 @@ def workload_config(args, world):
         "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
         "mode": args.mode, "difficulty": args.difficulty, "max_episode_steps": args.max_episode_steps,
         "obs_dtype": args.obs_dtype, "auto_reset": True,
-        "preroll_steps": max(args.preroll, 0),
+        "preroll_steps": resolved_preroll(args),
         "regime": "timed steps start after preroll + warmup steps, past the first episode timeout (desynchronised episodes)",
         "actions": f"pre-generated uniform int8 ids, {N_ACTION_SETS} arrays in HBM cycled",
         "parallelism": f"env-sharded x{world}, no collective in the step path",
@@ -487,8 +492,7 @@ def main():
     # pre-roll: with a short --warmup every timed step would lie inside the synchronised first episodes
     # (all envs time out together at step 500); these untimed steps put the timed region in the steady,
     # desynchronised regime the metric is defined on. ~0.7 s at 1 M envs.
-    preroll = args.preroll if args.preroll >= 0 else max(0, args.max_episode_steps + 100 - W)
-    args.preroll = preroll
+    preroll = resolved_preroll(args)
     for t in range(preroll + W):
         sim.step(acts[t % N_ACTION_SETS], None if acts2 is None else acts2[t % N_ACTION_SETS])
     torch.cuda.synchronize()

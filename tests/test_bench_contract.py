@@ -33,6 +33,27 @@ def test_reference_arm_line():
     assert "workload" in d["config"] and "model" not in d["config"]
 
 
+def test_reference_arm_prints_the_b200_arm_config_at_every_n():
+    """Under torchrun rank 0 of the reference arm describes the workload exactly as the B200 arm does at
+    that N (the driver compares the two `config` objects key for key)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    argv = ["--gpus", "2", "--steps", "2", "--warmup", "5", "--cpu-sample-envs", "512"]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"] + argv,
+                       capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    old = sys.argv
+    try:
+        sys.argv = ["bench.py"] + argv
+        want = bench.workload_config(bench.parse_args(), 2)
+    finally:
+        sys.argv = old
+    assert d["config"] == want and d["config"]["total_envs"] == 2 * d["config"]["envs_per_gpu"]
+    assert d["config"]["preroll_steps"] == 500 + 100 - 5 and d["n_gpus"] == 2
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
