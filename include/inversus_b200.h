@@ -204,6 +204,11 @@ int inv_get_host_path(const inv_sim *sim, int *nthreads, double *dma_fraction, d
  * rows [first, first+count), on nthreads host threads (AVX-512 / AVX2 non-temporal stores). */
 int inv_host_expand_f32(const uint32_t *bits, float *dst, int64_t first, int64_t count, int nthreads);
 
+/* The id check of the *_host calls, usable on its own (no GPU involved): copies ids[n] to staged[n]
+ * (staged may be ids itself) and returns INV_OK if every id is in 0..12, INV_ERR_INVALID_ACTION
+ * otherwise -- the ValueError of discrete_to_action, env_wrappers.py:66. One AVX2 pass. */
+int inv_host_stage_action_ids(const int8_t *ids, int8_t *staged, int64_t n);
+
 /* page-locked host memory for the *_host calls (pageable memory works too, slower) */
 int inv_host_alloc(void **out, int64_t nbytes);
 int inv_host_free(void *p);

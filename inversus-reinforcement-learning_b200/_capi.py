@@ -66,6 +66,7 @@ SYMBOLS = {
     "inv_set_host_path": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "inv_get_host_path": (C.c_int, [C.c_void_p, _P(C.c_int), _P(C.c_double), _P(C.c_double), _P(C.c_double)]),
     "inv_host_expand_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int]),
+    "inv_host_stage_action_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "inv_host_alloc": (C.c_int, [_P(C.c_void_p), C.c_int64]),
     "inv_host_free": (C.c_int, [C.c_void_p]),
     "inv_get_buffer": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_void_p), _P(C.c_int64)]),

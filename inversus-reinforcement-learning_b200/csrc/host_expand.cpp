@@ -139,7 +139,7 @@ __attribute__((target("avx2"))) static bool stage_ids_avx2(int8_t *dst, const in
 
 bool stage_action_ids(int8_t *dst, const int8_t *src, int64_t n)
 {
-    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    static const bool have_avx2 = __builtin_cpu_supports("avx2") && !getenv("INV_NO_AVX2");
     if (have_avx2) return stage_ids_avx2(dst, src, n);
     unsigned bad = 0;
     for (int64_t i = 0; i < n; ++i) {
@@ -166,3 +166,11 @@ extern "C" int inv_host_expand_f32(const uint32_t *bits, float *dst, int64_t fir
     return 0;
 }
 
+// C ABI: the id check of the *_host calls, usable on its own (no GPU involved). Copies ids[n] to
+// staged[n] (staged may equal ids) and returns 0 if every id is in 0..12, INV_ERR_INVALID_ACTION
+// (-3) otherwise -- discrete_to_action's ValueError, env_wrappers.py:66.
+extern "C" int inv_host_stage_action_ids(const int8_t *ids, int8_t *staged, int64_t n)
+{
+    if (!ids || !staged || n < 0) return -1;
+    return inv_host::stage_action_ids(staged, ids, n) ? -3 : 0;
+}

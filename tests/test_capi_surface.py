@@ -123,3 +123,39 @@ print("expand ok")
         env["INV_NO_AVX512"] = "1"
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "expand ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("no_avx2", [False, True])
+def test_host_side_action_id_check(no_avx2):
+    """inv_host_stage_action_ids (what every *_host call does before anything is enqueued): ids copied
+    verbatim, -3 exactly when an id is outside 0..12 -- at every position of the vector body and the
+    scalar tail, for negative ids too. Subprocess so that INV_NO_AVX2 selects the scalar path."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, sys, numpy as np
+sys.path.insert(0, %r)
+from inversus_b200 import _capi
+lib = _capi.load()
+rs = np.random.RandomState(1)
+for n in (0, 1, 31, 64, 65, 127, 128, 1000, 4097):
+    ids = rs.randint(0, 13, size=n).astype(np.int8)
+    out = np.full(n + 2, 99, np.int8)
+    dst = out[1:n + 1]
+    assert lib.inv_host_stage_action_ids(ids.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), n) == 0
+    assert np.array_equal(dst, ids) and out[0] == 99 and out[n + 1] == 99
+    for pos in sorted(set([0, n // 2, n - 1, max(n - 33, 0), min(63, max(n - 1, 0))])) if n else []:
+        for val in (13, 127, -1, -128):
+            bad = ids.copy()
+            bad[pos] = val
+            rc = lib.inv_host_stage_action_ids(bad.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), n)
+            assert rc == -3, (n, pos, val, rc)
+    twelve = np.full(n, 12, np.int8)            # the largest legal id everywhere
+    assert lib.inv_host_stage_action_ids(twelve.ctypes.data_as(C.c_void_p), twelve.ctypes.data_as(C.c_void_p), n) == 0
+print("ids ok")
+''' % ROOT
+    env = dict(os.environ)
+    if no_avx2:
+        env["INV_NO_AVX2"] = "1"
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "ids ok" in r.stdout, r.stdout + r.stderr
