@@ -179,7 +179,7 @@ typedef struct {
 } inv_episode_event;
 
 /* The step as a trainer with a GPU-resident policy consumes it: actions come from host memory, the
- * observations -- grid and extra -- stay on the device (inv_buffer), reward / done / info arrive
+ * observations -- grid and extra -- stay on the device (inv_get_buffer), reward / done / info arrive
  * dense (any may be NULL), and the episodes that ended in this step arrive as a compact list in env
  * order: *n_events records in events[0 .. capacity). 6 bytes per env plus 24 per finished episode
  * cross the bus instead of inv_step_host's 34 per env. capacity >= n_envs can never overflow; if
