@@ -560,8 +560,16 @@ def main():
             esim.reset()
         out = esim.host_buffers(pinned=True)
         rs = np.random.RandomState(args.seed + rank)
-        h_acts = [rs.randint(0, 13, size=ne).astype(np.int8) for _ in range(4)]
-        h_acts2 = [rs.randint(0, 13, size=ne).astype(np.int8) for _ in range(4)] if selfplay else None
+        pins = []
+
+        def host_ids():  # action ids in page-locked host memory (they go to the device from there)
+            t = torch.empty(ne, dtype=torch.int8, pin_memory=True)
+            pins.append(t)
+            a = t.numpy()
+            a[:] = rs.randint(0, 13, size=ne)
+            return a
+        h_acts = [host_ids() for _ in range(4)]
+        h_acts2 = [host_ids() for _ in range(4)] if selfplay else None
         views = 2 if selfplay else 1
         small = 4 + 1 + 1 + 4 + 8 + views * 16
 

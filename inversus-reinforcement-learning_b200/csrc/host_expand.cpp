@@ -137,6 +137,32 @@ __attribute__((target("avx2"))) static bool stage_ids_avx2(int8_t *dst, const in
     return bad != 0;
 }
 
+// the same check without the copy (ids that already sit in page-locked memory go to the device from there)
+__attribute__((target("avx2"))) static bool check_ids_avx2(const int8_t *src, int64_t n)
+{
+    const __m256i twelve = _mm256_set1_epi8(12);
+    __m256i bad0 = _mm256_setzero_si256(), bad1 = _mm256_setzero_si256();
+    int64_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 32));
+        bad0 = _mm256_or_si256(bad0, _mm256_xor_si256(_mm256_max_epu8(a, twelve), twelve));
+        bad1 = _mm256_or_si256(bad1, _mm256_xor_si256(_mm256_max_epu8(b, twelve), twelve));
+    }
+    unsigned bad = _mm256_testz_si256(_mm256_or_si256(bad0, bad1), _mm256_set1_epi8(-1)) ? 0u : 1u;
+    for (; i < n; ++i) bad |= (unsigned)((uint8_t)src[i] > 12);
+    return bad != 0;
+}
+
+bool check_action_ids(const int8_t *src, int64_t n)
+{
+    static const bool have_avx2 = __builtin_cpu_supports("avx2") && !getenv("INV_NO_AVX2");
+    if (have_avx2) return check_ids_avx2(src, n);
+    unsigned bad = 0;
+    for (int64_t i = 0; i < n; ++i) bad |= (unsigned)((uint8_t)src[i] > 12);
+    return bad != 0;
+}
+
 bool stage_action_ids(int8_t *dst, const int8_t *src, int64_t n)
 {
     static const bool have_avx2 = __builtin_cpu_supports("avx2") && !getenv("INV_NO_AVX2");
@@ -172,5 +198,6 @@ extern "C" int inv_host_expand_f32(const uint32_t *bits, float *dst, int64_t fir
 extern "C" int inv_host_stage_action_ids(const int8_t *ids, int8_t *staged, int64_t n)
 {
     if (!ids || !staged || n < 0) return -1;
+    if (staged == ids) return inv_host::check_action_ids(ids, n) ? -3 : 0; // in place: check only
     return inv_host::stage_action_ids(staged, ids, n) ? -3 : 0;
 }

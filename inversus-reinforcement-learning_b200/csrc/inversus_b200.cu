@@ -20,6 +20,7 @@ namespace inv_host { // host_expand.cpp
 void expand_f32(const uint32_t *bits, float *dst, int64_t lo, int64_t hi, int nthreads);
 int hardware_threads();
 bool stage_action_ids(int8_t *dst, const int8_t *src, int64_t n);
+bool check_action_ids(const int8_t *src, int64_t n);
 } // namespace inv_host
 
 struct inv_sim {
@@ -757,12 +758,28 @@ static int begin_host_step(inv_sim *s, const int8_t *a1, const int8_t *a2, const
     // discrete_to_action raises before anything is stepped (env_wrappers.py:302, :66): the ids are
     // checked in the same pass that moves them into the pinned staging buffer, and nothing has been
     // enqueued when the error is reported
-    bool bad = inv_host::stage_action_ids(s->h_a1, a1, n);
-    if (selfplay) bad |= inv_host::stage_action_ids(s->h_a2, a2, n);
+    // Ids the caller already keeps in page-locked memory are only checked and go up from where they
+    // are (the call synchronises before it returns, so the caller cannot change them under the copy).
+    auto page_locked = [](const void *p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const int8_t *src1 = s->h_a1, *src2 = s->h_a2;
+    bool bad;
+    if (page_locked(a1)) { bad = inv_host::check_action_ids(a1, n); src1 = a1; }
+    else bad = inv_host::stage_action_ids(s->h_a1, a1, n);
+    if (selfplay) {
+        if (page_locked(a2)) { bad |= inv_host::check_action_ids(a2, n); src2 = a2; }
+        else bad |= inv_host::stage_action_ids(s->h_a2, a2, n);
+    }
     if (bad) return fail(INV_ERR_INVALID_ACTION, "Invalid action_id: must be 0-12");
     if ((rc = order_host_stream(s)) != INV_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(s->d_a1, s->h_a1, (size_t)n, cudaMemcpyHostToDevice, s->host_stream));
-    if (selfplay) CUDA_TRY(cudaMemcpyAsync(s->d_a2, s->h_a2, (size_t)n, cudaMemcpyHostToDevice, s->host_stream));
+    CUDA_TRY(cudaMemcpyAsync(s->d_a1, src1, (size_t)n, cudaMemcpyHostToDevice, s->host_stream));
+    if (selfplay) CUDA_TRY(cudaMemcpyAsync(s->d_a2, src2, (size_t)n, cudaMemcpyHostToDevice, s->host_stream));
     return INV_OK;
 }
 

@@ -17,7 +17,10 @@ sim.reset()
 out = sim.host_buffers(pinned=True)
 small = {k: v for k, v in out.items() if not k.startswith("obs")}
 rs = np.random.RandomState(0)
-acts = [rs.randint(0, 13, size=n).astype(np.int8) for _ in range(4)]
+_pins = [torch.empty(n, dtype=torch.int8, pin_memory=True) for _ in range(4)]
+acts = [t.numpy() for t in _pins]
+for a in acts:
+    a[:] = rs.randint(0, 13, size=n)
 for what, bufs, steps in (("small outputs only", small, 30), ("full fp32 observations", out, 6)):
     for chunks in (1, 2, 4, 8):
         os.environ["INV_HOST_CHUNKS"] = str(chunks)

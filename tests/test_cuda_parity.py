@@ -220,7 +220,12 @@ def test_host_step_with_episode_events_matches_the_dense_outputs(n, chunks, monk
             if chunks > 1:
                 monkeypatch.setenv("INV_HOST_CHUNKS", str(chunks))
             eo["events"][:] = np.zeros(1, _capi.EVENT_DTYPE)[0]
-            ev = got.step_host_events(a1, a2, eo)
+            if t % 2:       # ids in page-locked memory go to the device from where they are
+                pa = torch.empty(n, dtype=torch.int8, pin_memory=True)
+                pa.numpy()[:] = a1
+                ev = got.step_host_events(pa.numpy(), a2, eo)
+            else:
+                ev = got.step_host_events(a1, a2, eo)
             for k in ("reward", "done", "info"):
                 assert np.array_equal(eo[k], ro[k]), (mode, t, k)
             idx = np.flatnonzero(ro["done"])
@@ -249,7 +254,8 @@ def test_host_step_with_episode_events_matches_the_dense_outputs(n, chunks, monk
         before = got.packed_state.clone()
         for pos, val in ((n - 1, 13), (5, -1), (n // 2, 127)):   # vector body and scalar tail of the id check
             with pytest.raises(ValueError):
-                bad = np.zeros(n, np.int8)
+                keep = torch.zeros(n, dtype=torch.int8, pin_memory=(pos == 5))  # both the staged and the direct path
+                bad = keep.numpy()
                 bad[pos] = val
                 got.step_host_events(np.zeros(n, np.int8) if mode == "selfplay" else bad,
                                      bad if mode == "selfplay" else None, eo)
